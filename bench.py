@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — graphs/sec through the 5-layer, 300-dim chem GIN forward+backward (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE configs[1]): the train() body of chem/pretrain_masking.py:46-70 on synthetic
+ZINC-shaped batches of 256 graphs — GNN(5, 300, JK="last", drop_ratio=0, "gin") in train mode,
+`linear_pred_atoms(node_rep[masked_atom_indices])`, cross-entropy on fp64 logits, `loss.backward()`.
+Optimizer steps are excluded; with N > 1 every rank draws its own batch (weak scaling,
+graphs sharded by rank) and the step includes ONE all-reduce of the flat fp32 gradient buffer.
+
+One JSON line is printed by rank 0.  `value` times K steps with the batch already resident in HBM
+(graph bucketing included: every step sees a different batch); `e2e` times the same K steps from pinned
+host tensors (H2D of x / edge_index / edge_attr / mask indices / labels inside the timed region, loss read
+back every step).  L2 is flushed between timed steps (256 MiB memset outside the per-step event pairs).
+`--impl reference` times the CPU oracle port of the reference's model.py on the host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 256
+NUM_LAYER, EMB = 5, 300
+NUM_DISTINCT_BATCHES = 8
+METRIC = "graphs/sec 5-layer GIN-300 fwd+bwd on ZINC-shaped batches"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batches(syn, rank, count):
+    out = []
+    for i in range(count):
+        seed = 2000 + 1000 * rank + i  # config-id*1000 + rank + batch index
+        b = syn.mask_atoms(syn.zinc_batch(BATCH, seed), seed)
+        out.append({k: b[k] for k in ("x", "edge_index", "edge_attr", "masked_atom_indices")} |
+                   {"labels": b["mask_node_label"][:, 0].contiguous()})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle port of chem/model.py + the masking head, all host threads
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_run(steps, warmup, threads=None, batches=None):
+    from oracle import gnn_oracle as O
+    syn = importlib.import_module("pretrain-gnns_b200.synthetic")
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    P = O.leaf_params(O.make_params("chem", "gin", NUM_LAYER, EMB, seed=1, randomize_bn=False))
+    g = torch.Generator().manual_seed(5)
+    W = (torch.randn(119, EMB, generator=g) * 0.05).requires_grad_(True)
+    bvec = torch.zeros(119, requires_grad=True)
+    batches = batches or make_batches(syn, 0, 2)
+
+    def step(b):
+        for v in list(P.values()) + [W, bvec]:
+            if v.requires_grad:
+                v.grad = None
+        rep = O.chem_gnn(P, b["x"], b["edge_index"], b["edge_attr"], NUM_LAYER, "gin", True)
+        loss, _ = O.masking_loss(rep, b["masked_atom_indices"], b["labels"], W, bvec)
+        loss.backward()
+        return float(loss.detach())
+
+    for i in range(warmup):
+        step(batches[i % len(batches)])
+    ts = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step(batches[i % len(batches)])
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return dict(value=BATCH * steps / total, ms_per_step=1e3 * total / steps, cores=threads,
+                sample="%d fwd+bwd steps of the B=%d masking batch (oracle port of chem/model.py, torch CPU, %d threads)"
+                       % (steps, BATCH, threads))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_oracle_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "chem pretrain_masking 5-layer GIN emb_dim=300 batch_size=256 (BASELINE configs[1])",
+                       "global_batch": BATCH, "note": "CPU oracle port; real torch_geometric 1.0.3 is not installable"},
+            "cpu_baseline": {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    syn = importlib.import_module("pretrain-gnns_b200.synthetic")
+    chem = importlib.import_module("pretrain-gnns_b200.chem.model")
+    ops = importlib.import_module("pretrain-gnns_b200.ops")
+    cabi = importlib.import_module("pretrain-gnns_b200._cabi")
+    pdist = importlib.import_module("pretrain-gnns_b200.dist")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback (use --impl reference)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if args.precision:
+        ops.set_precision(args.precision)
+    torch.manual_seed(0)
+    model = chem.GNN(NUM_LAYER, EMB, JK="last", drop_ratio=0, gnn_type="gin").to(dev).train()
+    head = torch.nn.Linear(EMB, 119).to(dev)
+    params = list(model.parameters()) + list(head.parameters())
+    reducer = pdist.GradAllReducer(params) if world > 1 else None
+
+    host = make_batches(syn, rank, NUM_DISTINCT_BATCHES)
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(b):
+        for p in params:
+            p.grad = None
+        rep = model(b["x"], b["edge_index"], b["edge_attr"])
+        logits = ops.linear(ops.row_gather(rep, b["masked_atom_indices"]), head.weight, head.bias)
+        loss = torch.nn.functional.cross_entropy(logits.double(), b["labels"])  # fp64 CE as the reference (:52)
+        loss.backward()
+        if reducer is not None:
+            reducer.all_reduce_mean()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.warmup):
+            b = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % len(pinned)].items()} if e2e else resident[i % len(resident)]
+            step(b).item()
+        barrier()
+        n0 = cabi.lib.pgnn_kernel_launch_count()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush, outside the per-step event pair
+            ev[i][0].record()
+            if e2e:
+                b = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % len(pinned)].items()}
+                step(b).item()   # D2H read of the loss every step, as chem/pretrain_masking.py:76 does
+            else:
+                step(resident[i % len(resident)])
+            ev[i][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        launches = cabi.lib.pgnn_kernel_launch_count() - n0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, wall
+
+    with ClockSampler(local_rank) as clocks:
+        ms_dev, launches, wall_dev = timed(False)
+        ms_e2e, _, wall_e2e = timed(True)
+    graphs = BATCH * world * args.steps
+
+    roof, roof_gather = kernel_rooflines(ops, cabi, resident[0], dev) if rank == 0 else (None, None)
+    cpu = cpu_oracle_run(6, 2, batches=host[:2]) if rank == 0 and not args.no_cpu_baseline else None
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": graphs / (ms_dev * 1e-3), "unit": "graphs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if ops.get_precision() == "fp32" else "tf32x3", "data": "synthetic",
+        "config": {"workload": "chem pretrain_masking 5-layer GIN emb_dim=300 batch_size=256 (BASELINE configs[1])",
+                   "global_batch": BATCH * world, "per_gpu_batch": BATCH, "parallelism": "dp%d" % world,
+                   "nodes_per_batch": int(host[0]["x"].shape[0]), "edges_per_batch": int(host[0]["edge_index"].shape[1]),
+                   "distinct_batches": NUM_DISTINCT_BATCHES, "l2": "flushed between timed steps (256 MiB memset)",
+                   "optimizer_step": "excluded (SURVEY 8(d))", "gemm_precision": ops.get_precision(),
+                   "wall_ms_per_step_incl_flush": 1e3 * wall_dev / args.steps},
+        "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof, "roofline_gather": roof_gather,
+        "cpu_baseline": None if cpu is None else {"value": cpu["value"], "unit": "graphs/s", "cores": cpu["cores"], "kind": "port",
+                                                  "sample": cpu["sample"]},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def kernel_rooflines(ops, cabi, b, dev):
+    """Isolated timings (CUDA events on the launch stream, L2 flushed before each launch) of the two kernels
+    the step is made of: the MLP GEMM (dominant, tensor/FMA-bound) and the neighbour gather (HBM/L2-bound)."""
+    pk = peaks()
+    n, e = int(b["x"].shape[0]), int(b["edge_index"].shape[1])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = ops.Graph(b["edge_index"], n)
+    S = g.summary("chem", ops.AGG_SUM, b["edge_attr"])
+    x = torch.randn(n, EMB, device=dev)
+    T = torch.randn(9, EMB, device=dev)
+    w1, b1 = torch.randn(2 * EMB, EMB, device=dev) * 0.05, torch.zeros(2 * EMB, device=dev)
+
+    def avg_ms(fn, reps=20):
+        fn(); torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); c.record(); c.synchronize()
+            tot += a.elapsed_time(c)
+        return tot / reps
+
+    with torch.no_grad():
+        t_gather = avg_ms(lambda: ops.aggregate(x, T, g, S, ops.AGG_SUM))
+        a = ops.aggregate(x, T, g, S, ops.AGG_SUM)
+        t_gemm = avg_ms(lambda: ops._linear_fwd(a, w1, b1, True))
+    gbytes = 4 * EMB * (e + 2 * n)              # rows read (E+N) + rows written N
+    gflop = 2.0 * n * EMB * 2 * EMB             # GEMM1 of the MLP: [N,300] x [300,600]
+    mode = ops.get_precision()
+    roof = {"bound": "tensor", "kernel": "MLP GEMM1 [N,300]x[300,600] (%s)" % mode, "achieved": gflop / (t_gemm * 1e-3) / 1e12,
+            "peak": pk["tensor"], "unit": "TFLOP/s", "frac": gflop / (t_gemm * 1e-3) / 1e12 / pk["tensor"], "traffic": None,
+            "peak_source": pk["src"] + " bf16 dense burst (tf32 dense is half of it; fp32 FFMA peak is ~72 TFLOP/s)",
+            "us_per_launch": t_gemm * 1e3}
+    roof_g = {"bound": "hbm", "kernel": "k_aggregate_fwd (gather + segment sum, one layer pass)", "achieved": gbytes / (t_gather * 1e-3) / 1e9,
+              "peak": pk["hbm"], "unit": "GB/s", "frac": gbytes / (t_gather * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+              "peak_source": pk["src"], "us_per_launch": t_gather * 1e3, "algorithmic_bytes": gbytes}
+    return roof, roof_g
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20  # bounded sample: ~0.2-0.3 s per CPU step
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,227 @@
+/*
+ * pgnn_b200.h — C ABI of libpgnn_b200.so: the B200 (sm_100a) message-passing hot path of
+ * snap-stanford/pretrain-gnns (chem/model.py, bio/model.py).
+ *
+ * The reference exposes NO native interface for this path: its arithmetic runs inside
+ * torch_geometric 1.0.3 / torch_scatter 1.1.2 / ATen (requirements.txt:2-7).  These entry points are
+ * what a binding for the path has to call; each one cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; row-major; fp32 unless noted
+ *   - `ld*` are row strides in ELEMENTS
+ *   - edge_index[0] is the aggregation TARGET, edge_index[1] the SOURCE (PyG 1.0.x flow)
+ *   - self-loops are implicit: every node has one, ordered after its real in-edges (chem/model.py:39)
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host sync), keep no
+ *     references to caller memory after the enqueued work completes, and are re-entrant per stream
+ *   - return 0 on success, a negative PGNN_E* code otherwise; nothing throws across the boundary
+ */
+#ifndef PGNN_B200_H
+#define PGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGNN_API __attribute__((visibility("default")))
+
+#define PGNN_OK 0
+#define PGNN_EINVAL (-1)      /* bad argument (null pointer, negative size, unsupported width) */
+#define PGNN_ECUDA (-2)       /* a CUDA call / launch failed; see pgnn_last_cuda_error() */
+#define PGNN_EWORKSPACE (-3)  /* workspace smaller than the *_workspace_bytes query */
+#define PGNN_EUNSUPPORTED (-4)
+
+/* reduction modes of the neighbour aggregation */
+#define PGNN_AGG_SUM 0   /* GIN:  chem/model.py:49,  bio/model.py:52            */
+#define PGNN_AGG_MEAN 1  /* SAGE: chem/model.py:169, bio/model.py:184 (count = in-degree + 1) */
+#define PGNN_AGG_GCN 2   /* GCN:  chem/model.py:73-82,103-104  w = deg^-1/2[t] * deg^-1/2[s] */
+
+PGNN_API int pgnn_version(void);
+PGNN_API const char* pgnn_error_string(int code);
+PGNN_API int pgnn_last_cuda_error(void);          /* cudaError_t of the last PGNN_ECUDA on this thread */
+PGNN_API int pgnn_device_sm_count(int device);   /* host query; negative on error */
+PGNN_API int64_t pgnn_kernel_launch_count(void); /* kernels this library has enqueued since load (process-wide) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph preparation (integer, bit-exact).  Replaces the per-layer, per-edge gather / scatter_add
+ * addressing done by MessagePassing.propagate (chem/model.py:49 [PyG 1.0.3]) with one bucketing per
+ * batch that all layers and both passes reuse.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Stable counting sort of `num_keys` int64 keys (stride `key_stride` elements) into `num_buckets`
+ * buckets.  rowptr[num_buckets+1]; order[num_keys] = original positions, bucket by bucket, ascending
+ * inside a bucket.  If vals != NULL (int64, stride val_stride), vals_out[p] = (int32) vals[order[p]].
+ * Keys outside [0, num_buckets) are undefined behaviour, as in the reference. */
+PGNN_API int64_t pgnn_bucket_workspace_bytes(int64_t num_keys, int64_t num_buckets);
+PGNN_API int pgnn_bucket(const int64_t* keys, int64_t key_stride, int64_t num_keys, int64_t num_buckets,
+                         const int64_t* vals, int64_t val_stride,
+                         int32_t* rowptr, int32_t* order, int32_t* vals_out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* edge_index int64 [2,E] -> by-target CSR (rowptr_t[N+1], nbr_t[E] = sources, eid_t[E]) and
+ * by-source CSR (rowptr_s, nbr_s = targets, eid_s).  Two pgnn_bucket passes. */
+PGNN_API int64_t pgnn_graph_prep_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+PGNN_API int pgnn_graph_prep(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                             int32_t* rowptr_t, int32_t* nbr_t, int32_t* eid_t,
+                             int32_t* rowptr_s, int32_t* nbr_s, int32_t* eid_s,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* dinv[i] = (in_degree(i) + 1)^-1/2  (GCN norm, chem/model.py:75-80; the +1 is the self-loop) */
+PGNN_API int pgnn_gcn_dinv(const int32_t* rowptr_t, int64_t num_nodes, float* dinv, void* stream);
+
+/* Per-node edge-feature summary S[N,Q]: because the message is LINEAR in the edge embedding, the
+ * per-edge embedding rows of chem/model.py:47 / bio/model.py:47 are never materialised:
+ *   sum_k w_k * e_k  =  S[i,:] . T      with T the [Q,C] table / transposed encoder (see aggregate).
+ * chem (Q = 9):  S[i,a] += w_k for bond type a = edge_attr[k,0] in 0..5, S[i,6+d] += w_k for direction d;
+ *                self-loop counts as type 4, direction 0 (chem/model.py:42-45).
+ * bio  (Q = 10): S[i,0:9] += w_k * edge_attr[k,0:9], self-loop adds w_ii to column 7 (bio/model.py:42-43);
+ *                S[i,9] = sum of weights (multiplies the encoder bias).
+ * w_k by `mode` (PGNN_AGG_*; dinv required for GCN). */
+PGNN_API int pgnn_chem_edge_summary(const int64_t* edge_attr /*[E,2]*/, const int32_t* rowptr_t,
+                                    const int32_t* nbr_t, const int32_t* eid_t, int64_t num_nodes,
+                                    int mode, const float* dinv, float* S /*[N,9]*/, void* stream);
+PGNN_API int pgnn_bio_edge_summary(const float* edge_attr /*[E,9]*/, const int32_t* rowptr_t,
+                                   const int32_t* nbr_t, const int32_t* eid_t, int64_t num_nodes,
+                                   int mode, const float* dinv, float* S /*[N,10]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input embeddings.  chem/model.py:264  h0 = E1[x[:,0]] + E2[x[:,1]];  bio/model.py:49-50
+ * h0 = E[(long) x] (one table, float-coded index).
+ * ------------------------------------------------------------------------------------------- */
+PGNN_API int pgnn_chem_embed_fwd(const int64_t* x /*[N,2]*/, const float* tab1, const float* tab2,
+                                 int64_t num_nodes, int64_t C, float* out, int64_t ldo, void* stream);
+/* gtab1 [rows1,C], gtab2 [rows2,C] are OVERWRITTEN (zeroed, then accumulated) */
+PGNN_API int pgnn_chem_embed_bwd(const int64_t* x, const float* g, int64_t ldg, int64_t num_nodes, int64_t C,
+                                 float* gtab1, int64_t rows1, float* gtab2, int64_t rows2, void* stream);
+PGNN_API int pgnn_bio_embed_fwd(const float* x /*[N]*/, const float* tab /*[2,C]*/, int64_t num_nodes,
+                                int64_t C, float* out, int64_t ldo, void* stream);
+PGNN_API int pgnn_bio_embed_bwd(const float* x, const float* g, int64_t ldg, int64_t num_nodes, int64_t C,
+                                float* gtab /*[2,C]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Neighbour aggregation (the gather + scatter_add of propagate, chem/model.py:49,101,196 and
+ * bio/model.py:52,111,218), atomics-free: one thread group per target row walks its bucket in edge
+ * order, self-loop last.
+ *
+ *   out[i, 0:C]           = sum_k w_k * x[nbr_t[k], 0:C] + w_ii * x[i, 0:C]   (+ S[i,:] . T if edge_off == 0)
+ *   out[i, edge_off: +C]  = S[i,:] . T                                       (if edge_off > 0: bio GIN concat,
+ *                                                                              bio/model.py:54-55)
+ * x may be given as (pre-BN activations, per-column affine, ReLU flag): x_eff = act(x * in_scale + in_shift)
+ * so a BatchNorm + ReLU (chem/model.py:269-275) is applied on load instead of in a pass of its own
+ * (in_scale == NULL -> identity).
+ * ------------------------------------------------------------------------------------------- */
+PGNN_API int pgnn_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift,
+                                int in_relu, int64_t num_nodes, int64_t C,
+                                const int32_t* rowptr_t, const int32_t* nbr_t, int mode, const float* dinv,
+                                const float* S, int64_t Q, const float* T /*[Q,C]*/, int64_t edge_off,
+                                float* out, int64_t ldo, void* stream);
+/* gx[j,0:C] = sum_{k: src_k = j} w_k * g[tgt_k, 0:C] + w_jj * g[j, 0:C]     (transpose-graph gather) */
+PGNN_API int pgnn_aggregate_bwd(const float* g, int64_t ldg, int64_t num_nodes, int64_t C,
+                                const int32_t* rowptr_s, const int32_t* nbr_s, int mode, const float* dinv,
+                                const int32_t* rowptr_t, float* gx, int64_t ldgx, void* stream);
+/* gT[Q,C] = S^T . g[:, g_off : g_off+C]   (edge-table / edge-encoder gradient; gT OVERWRITTEN) */
+PGNN_API int pgnn_edge_table_bwd(const float* S, int64_t Q, const float* g, int64_t ldg, int64_t g_off,
+                                 int64_t num_nodes, int64_t C, float* gT, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense node transforms (torch.nn.Linear inside GINConv.mlp chem/model.py:29, bio/model.py:24;
+ * GCN/SAGE/GAT linear chem/model.py:99,147,194).  precision: 0 = fp32 FFMA (SIMT),
+ * 1 = 3xTF32 error-compensated tcgen05 (falls back to 0 where a shape is unsupported).
+ * ------------------------------------------------------------------------------------------- */
+/* y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]) ; relu != 0 applies max(.,0) */
+PGNN_API int pgnn_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias,
+                             int64_t M, int64_t N, int64_t K, int relu, float* y, int64_t ldy,
+                             int precision, void* stream);
+/* gx[M,K] = (gy[M,N] . w[N,K]) * (relu_src > 0 ? 1 : 0)   relu_src: [M,K] activations or NULL */
+PGNN_API int pgnn_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t M, int64_t N, int64_t K,
+                               const float* relu_src, int64_t ldr, float* gx, int64_t ldgx,
+                               int precision, void* stream);
+/* gw[N,K] = gy[M,N]^T . x[M,K] ; gb[N] = column sums of gy (gb may be NULL).  Outputs OVERWRITTEN. */
+PGNN_API int pgnn_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t ldx,
+                               int64_t M, int64_t N, int64_t K, float* gw, float* gb,
+                               int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d (chem/model.py:252,269; bio/model.py:24), eps 1e-5, momentum 0.1 passed explicitly.
+ * Statistics are accumulated in fp64 (deterministic two-stage reduction, no atomics).
+ * ------------------------------------------------------------------------------------------- */
+PGNN_API int64_t pgnn_bn_workspace_bytes(int64_t M, int64_t C);
+/* train: batch statistics (biased var), y = act((x-mean)*invstd*gamma+beta); save_mean/save_invstd [C]
+ * written for backward; running_mean/var (unbiased var) and *num_batches_tracked updated in place
+ * when non-NULL.  y may be NULL (statistics only: the consumer applies scale/shift on load);
+ * scale/shift [C] (y = x*scale + shift) are written when non-NULL. */
+PGNN_API int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float momentum, float eps, int relu,
+                               float* y, int64_t ldy, float* save_mean, float* save_invstd,
+                               float* scale, float* shift, void* workspace, int64_t workspace_bytes,
+                               void* stream);
+PGNN_API int pgnn_bn_fwd_eval(const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                              const float* beta, const float* running_mean, const float* running_var,
+                              float eps, int relu, float* y, int64_t ldy, void* stream);
+/* gx = BN'(gy * relu_mask); ggamma/gbeta [C] OVERWRITTEN.  relu != 0: mask = (y > 0) with y recomputed
+ * from x, save_mean, save_invstd, gamma, beta. */
+PGNN_API int pgnn_bn_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t C,
+                         const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_invstd, int relu, float* gx, int64_t ldgx, float* ggamma,
+                         float* gbeta, void* workspace, int64_t workspace_bytes, void* stream);
+/* y = relu(x), gx = gy * (y > 0): the inter-layer ReLU of bio/model.py:281 (no BatchNorm there) */
+PGNN_API int pgnn_relu_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y, int64_t ldy, void* stream);
+PGNN_API int pgnn_relu_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_, int64_t M, int64_t C,
+                           float* gx, int64_t ldgx, void* stream);
+/* GraphSAGE update: y = x / max(||x||_2, 1e-12) per row (chem/model.py:201-202) and its backward */
+PGNN_API int pgnn_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y, int64_t ldy,
+                             float* norm /*[M]*/, void* stream);
+PGNN_API int pgnn_l2norm_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_, const float* norm,
+                             int64_t M, int64_t C, float* gx, int64_t ldgx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GAT (chem/model.py:134-165, bio/model.py:147-180), heads fixed by the caller (reference: 2).
+ * xl [N,H*D] is weight_linear(x).  Edge embedding rows e_k [H*D] are  Tsel = T rows selected/combined
+ * by the per-edge features: chem e_k = T[a0_k] + T[6 + a1_k] (T [9,H*D]); bio e_k = sum_q attr[k,q] T[q] +
+ * T[9] (T [10,H*D] = [W^T ; b]).  `feat` is the raw edge_attr (int64 [E,2] for chem, float [E,9] for bio).
+ * alpha [E+N, H] (bucket order per target then self-loop at E+i) is written for backward.
+ * ------------------------------------------------------------------------------------------- */
+PGNN_API int pgnn_gat_fwd(const float* xl, int64_t num_nodes, int64_t H, int64_t D, const float* att /*[H,2D]*/,
+                          const float* T, int is_bio, const void* feat, const int32_t* rowptr_t,
+                          const int32_t* nbr_t, const int32_t* eid_t, int64_t num_edges, const float* bias /*[D]*/,
+                          float slope, float* alpha, float* out /*[N,D]*/, int64_t ldo, void* stream);
+PGNN_API int64_t pgnn_gat_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t H, int64_t D);
+PGNN_API int pgnn_gat_bwd(const float* g /*[N,D]*/, int64_t ldg, const float* xl, int64_t num_nodes, int64_t H,
+                          int64_t D, const float* att, const float* T, int is_bio, const void* feat,
+                          const int32_t* rowptr_t, const int32_t* nbr_t, const int32_t* eid_t,
+                          const int32_t* rowptr_s, const int32_t* nbr_s, const int32_t* eid_s,
+                          int64_t num_edges, float slope, const float* alpha,
+                          float* gxl /*[N,H*D]*/, float* gatt /*[H,2D]*/, float* gT, float* gbias /*[D]*/,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heads (chem/model.py:326,369; chem/pretrain_masking.py:51,58-59; chem/pretrain_contextpred.py:54-67;
+ * bio/model.py:342-345).
+ * ------------------------------------------------------------------------------------------- */
+/* out[b,:] = mean of x rows whose segment id is b; `seg_ptr[B+1]`/`seg_order[N]` from pgnn_bucket(batch).
+ * Empty segments give 0 (count.clamp(min=1)). */
+PGNN_API int pgnn_segment_mean_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, const int32_t* seg_order,
+                                   int64_t num_seg, int64_t C, float* out, int64_t ldo, void* stream);
+/* gx[n,:] = g[seg[n],:] / max(count[seg[n]],1) ; seg = int64 ids [N] */
+PGNN_API int pgnn_segment_mean_bwd(const float* g, int64_t ldg, const int64_t* seg, const int32_t* seg_ptr,
+                                   int64_t num_rows, int64_t C, float* gx, int64_t ldgx, void* stream);
+/* out[m,:] = x[idx[m],:] (+ x[idx2[m],:] if idx2 != NULL: the bond representation rep[u]+rep[v]) */
+PGNN_API int pgnn_row_gather_fwd(const float* x, int64_t ldx, const int64_t* idx, const int64_t* idx2,
+                                 int64_t num_idx, int64_t C, float* out, int64_t ldo, void* stream);
+/* gx[idx[m],:] += g[m,:] (and idx2). gx must be pre-initialised by the caller (accumulates). */
+PGNN_API int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const int64_t* idx2,
+                                 int64_t num_idx, int64_t C, float* gx, int64_t ldgx, void* stream);
+/* out[r] = sum_d a[r,d] * b[(r + shift) mod B, d]   (cycle_index negatives, pretrain_contextpred.py:36-39,64-67) */
+PGNN_API int pgnn_shifted_rowdot_fwd(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t B, int64_t C,
+                                     int64_t shift, float* out, void* stream);
+/* ga[r,:] (+)= g[r] * b[(r+shift)%B,:] ; gb[r,:] (+)= g[(r-shift)%B] * a[(r-shift)%B,:] ; accumulate != 0 adds */
+PGNN_API int pgnn_shifted_rowdot_bwd(const float* g, const float* a, int64_t lda, const float* b, int64_t ldb,
+                                     int64_t B, int64_t C, int64_t shift, int accumulate,
+                                     float* ga, int64_t ldga, float* gb, int64_t ldgb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGNN_B200_H */

@@ -1,0 +1,337 @@
+// Neighbour aggregation kernels: the gather + scatter_add of MessagePassing.propagate
+// (chem/model.py:49,101,196; bio/model.py:52,111,218) restated as an atomics-free segmented
+// reduction over the target-bucketed edge list, plus its transpose and the edge-table gradients.
+//
+// Work decomposition: one thread per (row, float4 column) item.  D=300 rows are 75 float4, so a
+// warp-per-row mapping would idle 21 of 96 lane slots; flattening (row, c4) keeps every lane busy,
+// every load is a coalesced 16-byte access into the source row, and bucket metadata (rowptr / nbr)
+// is a warp-broadcast load.  Rows are 1200 B, so the whole activation matrix (7 MB at B=256) sits
+// in L2 after the first touch; see DESIGN.md for the roofline discussion.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 affine_act(float4 v, const float* __restrict__ sc, const float* __restrict__ sh,
+                                             int c, int relu) {
+  if (sc) {
+    const float4 a = ld4(sc + c), b = ld4(sh + c);
+    v.x = fmaf(v.x, a.x, b.x);
+    v.y = fmaf(v.y, a.y, b.y);
+    v.z = fmaf(v.z, a.z, b.z);
+    v.w = fmaf(v.w, a.w, b.w);
+  }
+  if (relu) {
+    v.x = fmaxf(v.x, 0.f);
+    v.y = fmaxf(v.y, 0.f);
+    v.z = fmaxf(v.z, 0.f);
+    v.w = fmaxf(v.w, 0.f);
+  }
+  return v;
+}
+
+// acc += w * v with separately rounded multiply and add: keeps the SUM path (w == 1) bit-identical to a
+// sequential CPU index_add_ in edge order, which the parity tests exploit.
+__device__ __forceinline__ void axpy4(float4& acc, float w, float4 v) {
+  acc.x = __fadd_rn(acc.x, __fmul_rn(w, v.x));
+  acc.y = __fadd_rn(acc.y, __fmul_rn(w, v.y));
+  acc.z = __fadd_rn(acc.z, __fmul_rn(w, v.z));
+  acc.w = __fadd_rn(acc.w, __fmul_rn(w, v.w));
+}
+__device__ __forceinline__ void add4(float4& acc, float4 v) {
+  acc.x = __fadd_rn(acc.x, v.x);
+  acc.y = __fadd_rn(acc.y, v.y);
+  acc.z = __fadd_rn(acc.z, v.z);
+  acc.w = __fadd_rn(acc.w, v.w);
+}
+
+__global__ void __launch_bounds__(256)
+k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restrict__ in_scale,
+                const float* __restrict__ in_shift, int in_relu, int64_t n, int C4, const int* __restrict__ rowptr,
+                const int* __restrict__ nbr, int mode, const float* __restrict__ dinv, const float* __restrict__ S, int Q,
+                const float* __restrict__ T, int64_t edge_off, float* __restrict__ out, int64_t ldo) {
+  const int64_t total = n * C4;
+  const int C = C4 * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / C4);
+    const int c = (int)(idx - (int64_t)i * C4) * 4;
+    const int lo = rowptr[i], hi = rowptr[i + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == PGNN_AGG_GCN) {
+      const float di = dinv[i];
+      for (int k = lo; k < hi; ++k) {
+        const int s = nbr[k];
+        axpy4(acc, __fmul_rn(di, dinv[s]), affine_act(ld4(x + (int64_t)s * ldx + c), in_scale, in_shift, c, in_relu));
+      }
+      axpy4(acc, __fmul_rn(di, di), affine_act(ld4(x + (int64_t)i * ldx + c), in_scale, in_shift, c, in_relu));
+    } else {
+      int k = lo;
+      for (; k + 1 < hi; k += 2) {  // two independent row loads in flight
+        const int s0 = nbr[k], s1 = nbr[k + 1];
+        const float4 v0 = ld4(x + (int64_t)s0 * ldx + c);
+        const float4 v1 = ld4(x + (int64_t)s1 * ldx + c);
+        add4(acc, affine_act(v0, in_scale, in_shift, c, in_relu));
+        add4(acc, affine_act(v1, in_scale, in_shift, c, in_relu));
+      }
+      if (k < hi) add4(acc, affine_act(ld4(x + (int64_t)nbr[k] * ldx + c), in_scale, in_shift, c, in_relu));
+      add4(acc, affine_act(ld4(x + (int64_t)i * ldx + c), in_scale, in_shift, c, in_relu));  // self-loop last
+      if (mode == PGNN_AGG_MEAN) {
+        const float cnt = (float)(hi - lo + 1);
+        acc.x = __fdiv_rn(acc.x, cnt);
+        acc.y = __fdiv_rn(acc.y, cnt);
+        acc.z = __fdiv_rn(acc.z, cnt);
+        acc.w = __fdiv_rn(acc.w, cnt);
+      }
+    }
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (S) {
+      const float* s = S + (int64_t)i * Q;
+      for (int q = 0; q < Q; ++q) {
+        const float w = s[q];
+        const float4 t = ld4(T + (int64_t)q * C + c);
+        e.x = fmaf(w, t.x, e.x);
+        e.y = fmaf(w, t.y, e.y);
+        e.z = fmaf(w, t.z, e.z);
+        e.w = fmaf(w, t.w, e.w);
+      }
+    }
+    if (edge_off == 0) {
+      add4(acc, e);
+      st4(out + (int64_t)i * ldo + c, acc);
+    } else {
+      st4(out + (int64_t)i * ldo + c, acc);
+      st4(out + (int64_t)i * ldo + edge_off + c, e);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_aggregate_bwd(const float* __restrict__ g, int64_t ldg, int64_t n, int C4, const int* __restrict__ rowptr_s,
+                const int* __restrict__ nbr_s, int mode, const float* __restrict__ dinv, const int* __restrict__ rowptr_t,
+                float* __restrict__ gx, int64_t ldgx) {
+  const int64_t total = n * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / C4);
+    const int c = (int)(idx - (int64_t)j * C4) * 4;
+    const int lo = rowptr_s[j], hi = rowptr_s[j + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == PGNN_AGG_SUM) {
+      int k = lo;
+      for (; k + 1 < hi; k += 2) {
+        const float4 v0 = ld4(g + (int64_t)nbr_s[k] * ldg + c);
+        const float4 v1 = ld4(g + (int64_t)nbr_s[k + 1] * ldg + c);
+        add4(acc, v0);
+        add4(acc, v1);
+      }
+      if (k < hi) add4(acc, ld4(g + (int64_t)nbr_s[k] * ldg + c));
+      add4(acc, ld4(g + (int64_t)j * ldg + c));
+    } else {
+      for (int k = lo; k < hi; ++k) {
+        const int t = nbr_s[k];
+        const float w = (mode == PGNN_AGG_MEAN) ? __frcp_rn((float)(rowptr_t[t + 1] - rowptr_t[t] + 1))
+                                                : __fmul_rn(dinv[t], dinv[j]);
+        axpy4(acc, w, ld4(g + (int64_t)t * ldg + c));
+      }
+      const float wl = (mode == PGNN_AGG_MEAN) ? __frcp_rn((float)(rowptr_t[j + 1] - rowptr_t[j] + 1))
+                                               : __fmul_rn(dinv[j], dinv[j]);
+      axpy4(acc, wl, ld4(g + (int64_t)j * ldg + c));
+    }
+    st4(gx + (int64_t)j * ldgx + c, acc);
+  }
+}
+
+// gT[q][c] = sum_i S[i][q] * g[i][g_off + c].  grid.x = row chunks, grid.y = 128-column tiles; each
+// thread owns one column and Q register accumulators, S rows are staged in shared memory; one fp32
+// atomicAdd per (chunk, q, c) folds the chunks.
+constexpr int kTblRows = 128;
+constexpr int kMaxQ = 16;
+__global__ void __launch_bounds__(128)
+k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g, int64_t ldg, int64_t g_off, int64_t n,
+                 int C, float* __restrict__ gT) {
+  __shared__ float s_S[kTblRows * kMaxQ];
+  const int64_t r0 = (int64_t)blockIdx.x * kTblRows;
+  const int rows = (int)((n - r0) < kTblRows ? (n - r0) : kTblRows);
+  for (int t = threadIdx.x; t < rows * Q; t += blockDim.x) s_S[t] = S[r0 * Q + t];
+  __syncthreads();
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= C) return;
+  float acc[kMaxQ];
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q) acc[q] = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float v = g[(r0 + r) * ldg + g_off + c];
+#pragma unroll
+    for (int q = 0; q < kMaxQ; ++q)
+      if (q < Q) acc[q] = fmaf(s_S[r * Q + q], v, acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q)
+    if (q < Q) atomicAdd(&gT[(int64_t)q * C + c], acc[q]);
+}
+
+__global__ void __launch_bounds__(256)
+k_chem_embed_fwd(const int64_t* __restrict__ x, const float* __restrict__ t1, const float* __restrict__ t2, int64_t n,
+                 int C4, float* __restrict__ out, int64_t ldo) {
+  const int64_t total = n * C4;
+  const int C = C4 * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / C4;
+    const int c = (int)(idx - i * C4) * 4;
+    const float4 a = ld4(t1 + x[2 * i] * C + c), b = ld4(t2 + x[2 * i + 1] * C + c);
+    st4(out + i * ldo + c, make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w)));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_chem_embed_bwd(const int64_t* __restrict__ x, const float* __restrict__ g, int64_t ldg, int64_t n, int C4,
+                 float* __restrict__ g1, float* __restrict__ g2) {
+  const int64_t total = n * C4;
+  const int C = C4 * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / C4;
+    const int c = (int)(idx - i * C4) * 4;
+    const float4 v = ld4(g + i * ldg + c);
+    atomicAdd(reinterpret_cast<float4*>(g1 + x[2 * i] * C + c), v);
+    atomicAdd(reinterpret_cast<float4*>(g2 + x[2 * i + 1] * C + c), v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bio_embed_fwd(const float* __restrict__ x, const float* __restrict__ tab, int64_t n, int C4, float* __restrict__ out,
+                int64_t ldo) {
+  const int64_t total = n * C4;
+  const int C = C4 * 4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / C4;
+    const int c = (int)(idx - i * C4) * 4;
+    st4(out + i * ldo + c, ld4(tab + (int64_t)x[i] * C + c));  // x.to(int64) truncates (bio/model.py:50)
+  }
+}
+
+// Two table rows only: each thread column-reduces a strided share of the nodes, one atomic per thread.
+__global__ void __launch_bounds__(256)
+k_bio_embed_bwd(const float* __restrict__ x, const float* __restrict__ g, int64_t ldg, int64_t n, int C,
+                float* __restrict__ gtab) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a0 = 0.f, a1 = 0.f;
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const float v = g[i * ldg + c];
+    if ((int64_t)x[i] == 0) a0 += v; else a1 += v;
+  }
+  atomicAdd(&gtab[c], a0);
+  atomicAdd(&gtab[C + c], a1);
+}
+
+inline int grid_items(int64_t items, int threads) {
+  int64_t b = ceil_div(items, threads);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int pgnn_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
+                       int64_t num_nodes, int64_t C, const int32_t* rowptr_t, const int32_t* nbr_t, int mode,
+                       const float* dinv, const float* S, int64_t Q, const float* T, int64_t edge_off, float* out, int64_t ldo,
+                       void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0 && mode >= 0 && mode <= 2);
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && rowptr_t && out && (mode != PGNN_AGG_GCN || dinv));
+  PGNN_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr));
+  PGNN_CHECK_ARG(!S || (T && Q > 0 && Q <= kMaxQ));
+  PGNN_CHECK_ARG(edge_off == 0 || (S && edge_off % 4 == 0));
+  if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out) || (T && !aligned16(T)) ||
+      (in_scale && (!aligned16(in_scale) || !aligned16(in_shift))))
+    return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_aggregate_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(
+      x, ldx, in_scale, in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t, mode, dinv, S, (int)Q, T, edge_off, out, ldo);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_aggregate_bwd(const float* g, int64_t ldg, int64_t num_nodes, int64_t C, const int32_t* rowptr_s,
+                       const int32_t* nbr_s, int mode, const float* dinv, const int32_t* rowptr_t, float* gx, int64_t ldgx,
+                       void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0 && mode >= 0 && mode <= 2);
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(g && rowptr_s && gx && (mode != PGNN_AGG_GCN || dinv) && (mode != PGNN_AGG_MEAN || rowptr_t));
+  if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_aggregate_bwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(g, ldg, num_nodes, C4, rowptr_s, nbr_s, mode,
+                                                                                 dinv, rowptr_t, gx, ldgx);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_edge_table_bwd(const float* S, int64_t Q, const float* g, int64_t ldg, int64_t g_off, int64_t num_nodes, int64_t C,
+                        float* gT, void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0 && Q > 0 && Q <= kMaxQ && gT);
+  cudaStream_t st = as_stream(stream);
+  PGNN_CUDA(cudaMemsetAsync(gT, 0, sizeof(float) * Q * C, st));
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(S && g);
+  dim3 grid((unsigned)ceil_div(num_nodes, kTblRows), (unsigned)ceil_div(C, 128));
+  k_edge_table_bwd<<<grid, 128, 0, st>>>(S, (int)Q, g, ldg, g_off, num_nodes, (int)C, gT);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_chem_embed_fwd(const int64_t* x, const float* tab1, const float* tab2, int64_t num_nodes, int64_t C, float* out,
+                        int64_t ldo, void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0);
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && tab1 && tab2 && out);
+  if (C % 4 || ldo % 4 || !aligned16(tab1) || !aligned16(tab2) || !aligned16(out)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_chem_embed_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(x, tab1, tab2, num_nodes, C4, out, ldo);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_chem_embed_bwd(const int64_t* x, const float* g, int64_t ldg, int64_t num_nodes, int64_t C, float* gtab1,
+                        int64_t rows1, float* gtab2, int64_t rows2, void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0 && gtab1 && gtab2 && rows1 > 0 && rows2 > 0);
+  cudaStream_t st = as_stream(stream);
+  PGNN_CUDA(cudaMemsetAsync(gtab1, 0, sizeof(float) * rows1 * C, st));
+  PGNN_CUDA(cudaMemsetAsync(gtab2, 0, sizeof(float) * rows2 * C, st));
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && g);
+  if (C % 4 || ldg % 4 || !aligned16(g) || !aligned16(gtab1) || !aligned16(gtab2)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_chem_embed_bwd<<<grid_items(num_nodes * C4, 256), 256, 0, st>>>(x, g, ldg, num_nodes, C4, gtab1, gtab2);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_bio_embed_fwd(const float* x, const float* tab, int64_t num_nodes, int64_t C, float* out, int64_t ldo, void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0);
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && tab && out);
+  if (C % 4 || ldo % 4 || !aligned16(tab) || !aligned16(out)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_bio_embed_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(x, tab, num_nodes, C4, out, ldo);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_bio_embed_bwd(const float* x, const float* g, int64_t ldg, int64_t num_nodes, int64_t C, float* gtab, void* stream) {
+  PGNN_CHECK_ARG(num_nodes >= 0 && C > 0 && gtab);
+  cudaStream_t st = as_stream(stream);
+  PGNN_CUDA(cudaMemsetAsync(gtab, 0, sizeof(float) * 2 * C, st));
+  if (num_nodes == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && g);
+  dim3 grid((unsigned)(num_nodes < 64 ? num_nodes : 64), (unsigned)ceil_div(C, 256));
+  k_bio_embed_bwd<<<grid, 256, 0, st>>>(x, g, ldg, num_nodes, (int)C, gtab);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+}  // extern "C"

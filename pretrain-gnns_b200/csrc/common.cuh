@@ -1,0 +1,54 @@
+// Shared helpers for libpgnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pgnn_b200.h"
+
+#include <atomic>
+extern thread_local int g_pgnn_last_cuda_error;
+extern std::atomic<long long> g_pgnn_kernel_launches;  // every kernel this library enqueues (pgnn_kernel_launch_count)
+
+#define PGNN_CHECK_ARG(cond)            \
+  do {                                  \
+    if (!(cond)) return PGNN_EINVAL;    \
+  } while (0)
+
+#define PGNN_CUDA(call)                       \
+  do {                                        \
+    cudaError_t e__ = (call);                 \
+    if (e__ != cudaSuccess) {                 \
+      g_pgnn_last_cuda_error = (int)e__;      \
+      return PGNN_ECUDA;                      \
+    }                                         \
+  } while (0)
+
+#define PGNN_LAUNCH_CHECK()                                        \
+  do {                                                             \
+    g_pgnn_kernel_launches.fetch_add(1, std::memory_order_relaxed); \
+    PGNN_CUDA(cudaGetLastError());                                 \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// B200: 148 SMs.  Grids for grid-stride kernels are sized as a multiple of this.
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// edge weight of the aggregation modes (PGNN_AGG_*), for target t with in-degree deg_t (real edges)
+__device__ __forceinline__ float agg_weight(int mode, const float* __restrict__ dinv, int t, int s, int deg_t) {
+  if (mode == PGNN_AGG_SUM) return 1.0f;
+  if (mode == PGNN_AGG_MEAN) return __frcp_rn((float)(deg_t + 1));
+  return __fmul_rn(dinv[t], dinv[s]);  // chem/model.py:82
+}

@@ -1,0 +1,194 @@
+// Graph-level and self-supervised heads: global_mean_pool (chem/model.py:326,369; bio/model.py:342),
+// row gathers for masked atoms / bonds / centre nodes (chem/pretrain_masking.py:51,58-59;
+// chem/pretrain_contextpred.py:54,57; bio/model.py:343) and the cyclic-shift negative-sampling dot
+// products (chem/pretrain_contextpred.py:36-39,64-67).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// one thread per (segment, float4 column); rows of a segment are walked in stable order
+__global__ void __launch_bounds__(256)
+k_segment_mean_fwd(const float* __restrict__ x, int64_t ldx, const int* __restrict__ seg_ptr, const int* __restrict__ seg_order,
+                   int64_t num_seg, int C4, float* __restrict__ out, int64_t ldo) {
+  const int64_t total = num_seg * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / C4;
+    const int c = (int)(idx - b * C4) * 4;
+    const int lo = seg_ptr[b], hi = seg_ptr[b + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = lo; k < hi; ++k) {
+      const float4 v = ld4(x + (int64_t)seg_order[k] * ldx + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float cnt = (float)max(hi - lo, 1);  // count.clamp(min=1)
+    st4(out + b * ldo + c, make_float4(acc.x / cnt, acc.y / cnt, acc.z / cnt, acc.w / cnt));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_segment_mean_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ seg, const int* __restrict__ seg_ptr,
+                   int64_t n, int C4, float* __restrict__ gx, int64_t ldgx) {
+  const int64_t total = n * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C4;
+    const int c = (int)(idx - r * C4) * 4;
+    const int64_t b = seg[r];
+    const float cnt = (float)max(seg_ptr[b + 1] - seg_ptr[b], 1);
+    const float4 v = ld4(g + b * ldg + c);
+    st4(gx + r * ldgx + c, make_float4(v.x / cnt, v.y / cnt, v.z / cnt, v.w / cnt));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_row_gather_fwd(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
+                 int64_t m, int C4, float* __restrict__ out, int64_t ldo) {
+  const int64_t total = m * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C4;
+    const int c = (int)(idx - r * C4) * 4;
+    float4 v = ld4(x + idx1[r] * ldx + c);
+    if (idx2) {
+      const float4 u = ld4(x + idx2[r] * ldx + c);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    st4(out + r * ldo + c, v);
+  }
+}
+
+// index_put_(accumulate=True): duplicates are legal (two masked bonds may share an atom), so rows are
+// accumulated with vector atomics (red.global.add.v4.f32).
+__global__ void __launch_bounds__(256)
+k_row_gather_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
+                 int64_t m, int C4, float* __restrict__ gx, int64_t ldgx) {
+  const int64_t total = m * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C4;
+    const int c = (int)(idx - r * C4) * 4;
+    const float4 v = ld4(g + r * ldg + c);
+    atomicAdd(reinterpret_cast<float4*>(gx + idx1[r] * ldgx + c), v);
+    if (idx2) atomicAdd(reinterpret_cast<float4*>(gx + idx2[r] * ldgx + c), v);
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256)
+k_shifted_rowdot_fwd(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, int64_t B, int C,
+                     int64_t shift, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < B; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int64_t rb = (r + shift) % B;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(a[r * lda + c], b[rb * ldb + c], s);
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_shifted_rowdot_bwd(const float* __restrict__ g, const float* __restrict__ a, int64_t lda, const float* __restrict__ b,
+                     int64_t ldb, int64_t B, int C, int64_t shift, int accumulate, float* __restrict__ ga, int64_t ldga,
+                     float* __restrict__ gb, int64_t ldgb) {
+  const int64_t total = B * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    const int64_t rf = (r + shift) % B;            // partner row of a[r]
+    const int64_t rbk = ((r - shift) % B + B) % B;  // row of a whose partner is b[r]
+    const float va = g[r] * b[rf * ldb + c];
+    const float vb = g[rbk] * a[rbk * lda + c];
+    if (accumulate) {
+      ga[r * ldga + c] += va;
+      gb[r * ldgb + c] += vb;
+    } else {
+      ga[r * ldga + c] = va;
+      gb[r * ldgb + c] = vb;
+    }
+  }
+}
+
+inline int grid_items(int64_t items, int threads) {
+  int64_t b = ceil_div(items, threads);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int pgnn_segment_mean_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, const int32_t* seg_order, int64_t num_seg,
+                          int64_t C, float* out, int64_t ldo, void* stream) {
+  PGNN_CHECK_ARG(num_seg >= 0 && C > 0);
+  if (num_seg == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(seg_ptr && out);
+  if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_segment_mean_fwd<<<grid_items(num_seg * C4, 256), 256, 0, as_stream(stream)>>>(x, ldx, seg_ptr, seg_order, num_seg, C4, out,
+                                                                                   ldo);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_segment_mean_bwd(const float* g, int64_t ldg, const int64_t* seg, const int32_t* seg_ptr, int64_t num_rows, int64_t C,
+                          float* gx, int64_t ldgx, void* stream) {
+  PGNN_CHECK_ARG(num_rows >= 0 && C > 0);
+  if (num_rows == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(g && seg && seg_ptr && gx);
+  if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_segment_mean_bwd<<<grid_items(num_rows * C4, 256), 256, 0, as_stream(stream)>>>(g, ldg, seg, seg_ptr, num_rows, C4, gx, ldgx);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_row_gather_fwd(const float* x, int64_t ldx, const int64_t* idx, const int64_t* idx2, int64_t num_idx, int64_t C,
+                        float* out, int64_t ldo, void* stream) {
+  PGNN_CHECK_ARG(num_idx >= 0 && C > 0);
+  if (num_idx == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && idx && out);
+  if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_row_gather_fwd<<<grid_items(num_idx * C4, 256), 256, 0, as_stream(stream)>>>(x, ldx, idx, idx2, num_idx, C4, out, ldo);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const int64_t* idx2, int64_t num_idx, int64_t C,
+                        float* gx, int64_t ldgx, void* stream) {
+  PGNN_CHECK_ARG(num_idx >= 0 && C > 0);
+  if (num_idx == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(g && idx && gx);
+  if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_row_gather_bwd<<<grid_items(num_idx * C4, 256), 256, 0, as_stream(stream)>>>(g, ldg, idx, idx2, num_idx, C4, gx, ldgx);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_shifted_rowdot_fwd(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t B, int64_t C, int64_t shift,
+                            float* out, void* stream) {
+  PGNN_CHECK_ARG(B >= 0 && C > 0 && shift >= 0);
+  if (B == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(a && b && out);
+  k_shifted_rowdot_fwd<<<grid_items(B * 32, 256), 256, 0, as_stream(stream)>>>(a, lda, b, ldb, B, (int)C, shift, out);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_shifted_rowdot_bwd(const float* g, const float* a, int64_t lda, const float* b, int64_t ldb, int64_t B, int64_t C,
+                            int64_t shift, int accumulate, float* ga, int64_t ldga, float* gb, int64_t ldgb, void* stream) {
+  PGNN_CHECK_ARG(B >= 0 && C > 0 && shift >= 0);
+  if (B == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(g && a && b && ga && gb);
+  k_shifted_rowdot_bwd<<<grid_items(B * C, 256), 256, 0, as_stream(stream)>>>(g, a, lda, b, ldb, B, (int)C, shift, accumulate, ga,
+                                                                             ldga, gb, ldgb);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// BatchNorm1d (chem/model.py:252,269; bio/model.py:24), the inter-layer ReLU (bio/model.py:281) and
+// GraphSAGE's row L2-normalisation (chem/model.py:201-202), forward and backward.
+//
+// Column statistics are a grid-wide dependency.  They are reduced in two deterministic stages:
+// per-(row-chunk, column) partial sums in fp64 -> one finalize pass that walks the chunks in order.
+// fp64 accumulation makes E[x^2]-E[x]^2 safe (relative error ~1e-16 * mean^2/var) and costs nothing
+// measurable at [N<=40k, C<=600].
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxChunks = 2 * kNumSMs;  // 296 row chunks at most
+
+struct Chunking { int chunks, rows_per; };
+inline Chunking chunking(int64_t M) {
+  int64_t chunks = ceil_div(M, 32);
+  if (chunks > kMaxChunks) chunks = kMaxChunks;
+  if (chunks < 1) chunks = 1;
+  const int64_t rows_per = ceil_div(M, chunks);
+  chunks = ceil_div(M, rows_per);
+  return {(int)chunks, (int)rows_per};
+}
+
+__global__ void __launch_bounds__(128)
+k_bn_partial(const float* __restrict__ x, int64_t ldx, int M, int C, int rows_per, double* __restrict__ part) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  double s = 0.0, ss = 0.0;
+  for (int r = r0; r < r1; ++r) {
+    const double v = (double)x[(int64_t)r * ldx + c];
+    s += v;
+    ss += v * v;
+  }
+  part[((int64_t)blockIdx.y * 2 + 0) * C + c] = s;
+  part[((int64_t)blockIdx.y * 2 + 1) * C + c] = ss;
+}
+
+__global__ void __launch_bounds__(128)
+k_bn_finalize(const double* __restrict__ part, int chunks, int M, int C, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+              int64_t* __restrict__ nbt, float momentum, float eps, float* __restrict__ save_mean,
+              float* __restrict__ save_invstd, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s += part[((int64_t)k * 2 + 0) * C + c];
+    ss += part[((int64_t)k * 2 + 1) * C + c];
+  }
+  const double mean = s / M;
+  double var = ss / M - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  if (save_mean) save_mean[c] = meanf;
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * meanf;
+  if (running_var) {
+    const double unbiased = var * ((double)M / (double)(M > 1 ? M - 1 : 1));
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+  if (scale) {
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = fmaf(-meanf, sc, beta[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const float* __restrict__ mean,
+           const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+           float* __restrict__ y, int64_t ldy) {
+  const int64_t total = M * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    float v = fmaf((x[r * ldx + c] - mean[c]) * invstd[c], gamma[c], beta[c]);
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * ldy + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_eval(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const float* __restrict__ gamma,
+          const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps, int relu,
+          float* __restrict__ y, int64_t ldy) {
+  const int64_t total = M * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    const float invstd = __frcp_rn(__fsqrt_rn(rv[c] + eps));
+    float v = fmaf((x[r * ldx + c] - rm[c]) * invstd, gamma[c], beta[c]);
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * ldy + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_bn_bwd_partial(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
+                 int rows_per, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                 const float* __restrict__ invstd, int relu, double* __restrict__ part) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+  double s = 0.0, sx = 0.0;
+  for (int r = r0; r < r1; ++r) {
+    const float xhat = (x[(int64_t)r * ldx + c] - mu) * is;
+    float d = gy[(int64_t)r * ldgy + c];
+    if (relu && !(fmaf(xhat, ga, be) > 0.f)) d = 0.f;
+    s += (double)d;
+    sx += (double)d * (double)xhat;
+  }
+  part[((int64_t)blockIdx.y * 2 + 0) * C + c] = s;
+  part[((int64_t)blockIdx.y * 2 + 1) * C + c] = sx;
+}
+
+__global__ void __launch_bounds__(128)
+k_bn_bwd_finalize(const double* __restrict__ part, int chunks, int M, int C, float* __restrict__ ggamma,
+                  float* __restrict__ gbeta, float* __restrict__ c1, float* __restrict__ c2) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s += part[((int64_t)k * 2 + 0) * C + c];
+    sx += part[((int64_t)k * 2 + 1) * C + c];
+  }
+  if (gbeta) gbeta[c] = (float)s;
+  if (ggamma) ggamma[c] = (float)sx;
+  c1[c] = (float)(s / M);
+  c2[c] = (float)(sx / M);
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int64_t M, int C,
+               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+               const float* __restrict__ invstd, int relu, const float* __restrict__ c1, const float* __restrict__ c2,
+               float* __restrict__ gx, int64_t ldgx) {
+  const int64_t total = M * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    const float xhat = (x[r * ldx + c] - mean[c]) * invstd[c];
+    float d = gy[r * ldgy + c];
+    if (relu && !(fmaf(xhat, gamma[c], beta[c]) > 0.f)) d = 0.f;
+    gx[r * ldgx + c] = gamma[c] * invstd[c] * (d - c1[c] - xhat * c2[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_relu_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy) {
+  const int64_t total = M * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    y[r * ldy + c] = fmaxf(x[r * ldx + c], 0.f);
+  }
+}
+__global__ void __launch_bounds__(256)
+k_relu_bwd(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ y, int64_t ldy, int64_t M, int C,
+           float* __restrict__ gx, int64_t ldgx) {
+  const int64_t total = M * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    gx[r * ldgx + c] = y[r * ldy + c] > 0.f ? gy[r * ldgy + c] : 0.f;
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256)
+k_l2norm_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy,
+             float* __restrict__ norm) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = x[r * ldx + c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+    if (lane == 0) norm[r] = nrm;
+    for (int c = lane; c < C; c += 32) y[r * ldy + c] = x[r * ldx + c] / nrm;
+  }
+}
+__global__ void __launch_bounds__(256)
+k_l2norm_bwd(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ y, int64_t ldy, const float* __restrict__ norm,
+             int64_t M, int C, float* __restrict__ gx, int64_t ldgx) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    float dot = 0.f;
+    for (int c = lane; c < C; c += 32) dot = fmaf(gy[r * ldgy + c], y[r * ldy + c], dot);
+    dot = warp_sum(dot);
+    const float nrm = norm[r];
+    // y = x / n with n = max(||x||, eps); for ||x|| > eps: gx = (gy - y * <gy, y>) / n; below eps n is constant
+    const bool clamped = nrm <= 1e-12f;
+    for (int c = lane; c < C; c += 32) {
+      const float g = gy[r * ldgy + c];
+      gx[r * ldgx + c] = clamped ? g / nrm : (g - y[r * ldy + c] * dot) / nrm;
+    }
+  }
+}
+
+inline int grid_items(int64_t items, int threads) {
+  int64_t b = ceil_div(items, threads);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t pgnn_bn_workspace_bytes(int64_t M, int64_t C) {
+  if (M < 0 || C <= 0) return PGNN_EINVAL;
+  return align_up((int64_t)kMaxChunks * 2 * C * 8, 256) + align_up(2 * C * 4, 256);
+}
+
+int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int relu,
+                      float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale, float* shift, void* workspace,
+                      int64_t workspace_bytes, void* stream) {
+  PGNN_CHECK_ARG(M > 0 && C > 0 && M < (1ll << 31) && x && gamma && beta && save_mean && save_invstd && workspace);
+  PGNN_CHECK_ARG((scale == nullptr) == (shift == nullptr));
+  if (workspace_bytes < pgnn_bn_workspace_bytes(M, C)) return PGNN_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  double* part = reinterpret_cast<double*>(workspace);
+  const Chunking ch = chunking(M);
+  dim3 g1((unsigned)ceil_div(C, 128), (unsigned)ch.chunks);
+  k_bn_partial<<<g1, 128, 0, st>>>(x, ldx, (int)M, (int)C, ch.rows_per, part);
+  PGNN_LAUNCH_CHECK();
+  k_bn_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(part, ch.chunks, (int)M, (int)C, gamma, beta, running_mean,
+                                                           running_var, num_batches_tracked, momentum, eps, save_mean,
+                                                           save_invstd, scale, shift);
+  PGNN_LAUNCH_CHECK();
+  if (y) {
+    k_bn_apply<<<grid_items(M * C, 256), 256, 0, st>>>(x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy);
+    PGNN_LAUNCH_CHECK();
+  }
+  return PGNN_OK;
+}
+
+int pgnn_bn_fwd_eval(const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma, const float* beta,
+                     const float* running_mean, const float* running_var, float eps, int relu, float* y, int64_t ldy,
+                     void* stream) {
+  PGNN_CHECK_ARG(M >= 0 && C > 0);
+  if (M == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && gamma && beta && running_mean && running_var && y);
+  k_bn_eval<<<grid_items(M * C, 256), 256, 0, as_stream(stream)>>>(x, ldx, M, (int)C, gamma, beta, running_mean, running_var, eps,
+                                                                    relu, y, ldy);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_bn_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                const float* beta, const float* save_mean, const float* save_invstd, int relu, float* gx, int64_t ldgx,
+                float* ggamma, float* gbeta, void* workspace, int64_t workspace_bytes, void* stream) {
+  PGNN_CHECK_ARG(M > 0 && C > 0 && M < (1ll << 31) && gy && x && gamma && beta && save_mean && save_invstd && gx && workspace);
+  if (workspace_bytes < pgnn_bn_workspace_bytes(M, C)) return PGNN_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  double* part = reinterpret_cast<double*>(workspace);
+  float* c1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up((int64_t)kMaxChunks * 2 * C * 8, 256));
+  float* c2 = c1 + C;
+  const Chunking ch = chunking(M);
+  dim3 g1((unsigned)ceil_div(C, 128), (unsigned)ch.chunks);
+  k_bn_bwd_partial<<<g1, 128, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, ch.rows_per, gamma, beta, save_mean, save_invstd, relu,
+                                       part);
+  PGNN_LAUNCH_CHECK();
+  k_bn_bwd_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(part, ch.chunks, (int)M, (int)C, ggamma, gbeta, c1, c2);
+  PGNN_LAUNCH_CHECK();
+  k_bn_bwd_apply<<<grid_items(M * C, 256), 256, 0, st>>>(gy, ldgy, x, ldx, M, (int)C, gamma, beta, save_mean, save_invstd, relu,
+                                                        c1, c2, gx, ldgx);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_relu_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y, int64_t ldy, void* stream) {
+  PGNN_CHECK_ARG(M >= 0 && C > 0);
+  if (M == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && y);
+  k_relu_fwd<<<grid_items(M * C, 256), 256, 0, as_stream(stream)>>>(x, ldx, M, (int)C, y, ldy);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_relu_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_, int64_t M, int64_t C, float* gx, int64_t ldgx,
+                  void* stream) {
+  PGNN_CHECK_ARG(M >= 0 && C > 0);
+  if (M == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(gy && y && gx);
+  k_relu_bwd<<<grid_items(M * C, 256), 256, 0, as_stream(stream)>>>(gy, ldgy, y, ldy_, M, (int)C, gx, ldgx);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y, int64_t ldy, float* norm, void* stream) {
+  PGNN_CHECK_ARG(M >= 0 && C > 0);
+  if (M == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(x && y && norm);
+  k_l2norm_fwd<<<grid_items(M * 32, 256), 256, 0, as_stream(stream)>>>(x, ldx, M, (int)C, y, ldy, norm);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_l2norm_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_, const float* norm, int64_t M, int64_t C,
+                    float* gx, int64_t ldgx, void* stream) {
+  PGNN_CHECK_ARG(M >= 0 && C > 0);
+  if (M == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(gy && y && norm && gx);
+  k_l2norm_bwd<<<grid_items(M * 32, 256), 256, 0, as_stream(stream)>>>(gy, ldgy, y, ldy_, norm, M, (int)C, gx, ldgx);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+}  // extern "C"

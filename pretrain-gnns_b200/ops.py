@@ -1,0 +1,512 @@
+"""Host-side operators: torch tensors in, C-ABI calls out (device pointers + the current CUDA stream).
+
+Every function here is a thin `torch.autograd.Function` (or plain call) around one or two entry points
+of `include/pgnn_b200.h`.  torch is used for device memory, the stream and autograd bookkeeping only;
+all arithmetic on the path happens in libpgnn_b200.so.  Host tensors are rejected: there is no CPU
+fallback.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.autograd import Function
+
+from ._cabi import PgnnError, check, lib
+
+AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
+_PRECISION = {"fp32": 0, "tf32x3": 1}
+_precision = _PRECISION.get(os.environ.get("PGNN_PRECISION", "fp32"), 0)
+
+
+def set_precision(name: str):
+    """'fp32' = FFMA SIMT GEMMs (exact fp32); 'tf32x3' = error-compensated 3xTF32 tcgen05 GEMMs."""
+    global _precision
+    _precision = _PRECISION[name]
+
+
+def get_precision() -> str:
+    return "tf32x3" if _precision == 1 else "fp32"
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PgnnError("pretrain-gnns_b200 runs on CUDA tensors only: no CPU fallback exists for this path "
+                            "(got a %s tensor)" % t.device)
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise PgnnError("fp32 tensors expected, got %s" % t.dtype)
+    return t if t.stride(-1) == 1 and (t.dim() < 2 or t.stride(0) >= t.shape[1]) else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# graph preparation
+# ------------------------------------------------------------------------------------------------
+class Graph:
+    """Target- and source-bucketed CSR of one batch (pgnn_graph_prep), shared by all layers/passes."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        _dev(edge_index)
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise PgnnError("edge_index must be int64 [2, E]")
+        ei = edge_index.contiguous()
+        n, e = int(num_nodes), int(ei.shape[1])
+        dev = ei.device
+        self.n, self.e, self.device = n, e, dev
+        self._edge_index = ei  # keeps the storage alive while this object is cached
+        i32 = dict(dtype=torch.int32, device=dev)
+        buf = torch.empty(2 * (n + 1) + 4 * max(e, 1), **i32)
+        o = 0
+        self.rowptr_t = buf[o:o + n + 1]; o += n + 1
+        self.rowptr_s = buf[o:o + n + 1]; o += n + 1
+        self.nbr_t = buf[o:o + e]; o += max(e, 1)
+        self.eid_t = buf[o:o + e]; o += max(e, 1)
+        self.nbr_s = buf[o:o + e]; o += max(e, 1)
+        self.eid_s = buf[o:o + e]
+        wsb = lib.pgnn_graph_prep_workspace_bytes(n, e)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.pgnn_graph_prep(_p(ei), e, n, _p(self.rowptr_t), _p(self.nbr_t), _p(self.eid_t), _p(self.rowptr_s),
+                                  _p(self.nbr_s), _p(self.eid_s), _p(ws), wsb, _st()), "graph_prep")
+        self._dinv = None
+        self._summaries = {}
+
+    @property
+    def dinv(self):
+        if self._dinv is None:
+            self._dinv = torch.empty(self.n, dtype=torch.float32, device=self.device)
+            check(lib.pgnn_gcn_dinv(_p(self.rowptr_t), self.n, _p(self._dinv), _st()), "gcn_dinv")
+        return self._dinv
+
+    def summary(self, domain: str, mode: int, edge_attr: torch.Tensor) -> torch.Tensor:
+        """S [N,9] (chem) / [N,10] (bio) edge-feature summary for this aggregation mode (cached per batch)."""
+        key = (domain, mode)
+        hit = self._summaries.get(key)
+        if hit is not None and hit[0] is edge_attr and hit[1] == edge_attr._version:
+            return hit[2]
+        _dev(edge_attr)
+        ea = edge_attr.contiguous()
+        dinv = self.dinv if mode == AGG_GCN else None
+        if domain == "chem":
+            if ea.dtype != torch.int64 or ea.shape != (self.e, 2):
+                raise PgnnError("chem edge_attr must be int64 [E, 2]")
+            S = torch.empty(self.n, 9, dtype=torch.float32, device=self.device)
+            check(lib.pgnn_chem_edge_summary(_p(ea), _p(self.rowptr_t), _p(self.nbr_t), _p(self.eid_t), self.n, mode,
+                                             _p(dinv), _p(S), _st()), "chem_edge_summary")
+        else:
+            if ea.dtype != torch.float32 or ea.shape != (self.e, 9):
+                raise PgnnError("bio edge_attr must be float32 [E, 9]")
+            S = torch.empty(self.n, 10, dtype=torch.float32, device=self.device)
+            check(lib.pgnn_bio_edge_summary(_p(ea), _p(self.rowptr_t), _p(self.nbr_t), _p(self.eid_t), self.n, mode,
+                                            _p(dinv), _p(S), _st()), "bio_edge_summary")
+        self._summaries[key] = (edge_attr, edge_attr._version, S)
+        return S
+
+
+_graph_cache = [None]
+
+
+def graph_for(edge_index: torch.Tensor, num_nodes: int) -> Graph:
+    """One-entry cache so that convs called layer by layer on the same batch bucket it once.  The entry
+    holds the edge_index tensor itself, so an address match can only be the same live storage; in-place
+    edits bump `_version` and invalidate it."""
+    hit = _graph_cache[0]
+    if hit is not None and hit[0] is edge_index and hit[1] == edge_index._version and hit[2].n == num_nodes:
+        return hit[2]
+    g = Graph(edge_index, num_nodes)
+    _graph_cache[0] = (edge_index, edge_index._version, g)
+    return g
+
+
+def clear_graph_cache():
+    _graph_cache[0] = None
+
+
+class Segments:
+    """`batch`-style assignment vector bucketed by segment id (pgnn_bucket): rowptr + stable order."""
+
+    def __init__(self, seg: torch.Tensor, num_seg: int):
+        _dev(seg)
+        if seg.dtype != torch.int64 or seg.dim() != 1:
+            raise PgnnError("segment ids must be int64 [N]")
+        self.seg = seg.contiguous()
+        n = int(seg.shape[0])
+        self.n, self.num_seg = n, int(num_seg)
+        self.ptr = torch.empty(self.num_seg + 1, dtype=torch.int32, device=seg.device)
+        self.order = torch.empty(max(n, 1), dtype=torch.int32, device=seg.device)
+        wsb = lib.pgnn_bucket_workspace_bytes(n, self.num_seg)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=seg.device)
+        check(lib.pgnn_bucket(_p(self.seg), 1, n, self.num_seg, None, 0, _p(self.ptr), _p(self.order), None, _p(ws),
+                              wsb, _st()), "bucket")
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------
+class _Aggregate(Function):
+    @staticmethod
+    def forward(ctx, x, T, graph, S, mode, concat):
+        _dev(x, T)
+        x, T = _f32(x), _f32(T).contiguous()
+        n, C = x.shape
+        Q = T.shape[0]
+        out = torch.empty(n, 2 * C if concat else C, dtype=torch.float32, device=x.device)
+        dinv = graph.dinv if mode == AGG_GCN else None
+        check(lib.pgnn_aggregate_fwd(_p(x), x.stride(0), None, None, 0, n, C, _p(graph.rowptr_t), _p(graph.nbr_t), mode,
+                                     _p(dinv), _p(S), Q, _p(T), C if concat else 0, _p(out), out.stride(0), _st()),
+              "aggregate_fwd")
+        ctx.graph, ctx.S, ctx.mode, ctx.concat, ctx.C, ctx.Q = graph, S, mode, concat, C, Q
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        graph, n, C, Q = ctx.graph, ctx.graph.n, ctx.C, ctx.Q
+        gx = gT = None
+        dinv = graph.dinv if ctx.mode == AGG_GCN else None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(n, C, dtype=torch.float32, device=g.device)
+            check(lib.pgnn_aggregate_bwd(_p(g), g.stride(0), n, C, _p(graph.rowptr_s), _p(graph.nbr_s), ctx.mode, _p(dinv),
+                                         _p(graph.rowptr_t), _p(gx), C, _st()), "aggregate_bwd")
+        if ctx.needs_input_grad[1]:
+            gT = torch.empty(Q, C, dtype=torch.float32, device=g.device)
+            check(lib.pgnn_edge_table_bwd(_p(ctx.S), Q, _p(g), g.stride(0), C if ctx.concat else 0, n, C, _p(gT), _st()),
+                  "edge_table_bwd")
+        return gx, gT, None, None, None, None
+
+
+def aggregate(x, T, graph, S, mode=AGG_SUM, concat=False):
+    return _Aggregate.apply(x, T, graph, S, mode, concat)
+
+
+def _linear_fwd(x, w, b, relu):
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    check(lib.pgnn_linear_fwd(_p(x), x.stride(0), _p(w), _p(b), M, N, K, int(relu), _p(y), N, _precision, _st()), "linear_fwd")
+    return y
+
+
+def _linear_bwd_x(gy, w, mask=None):
+    M, N = gy.shape
+    K = w.shape[1]
+    gx = torch.empty(M, K, dtype=torch.float32, device=gy.device)
+    check(lib.pgnn_linear_bwd_x(_p(gy), gy.stride(0), _p(w), M, N, K, _p(mask), 0 if mask is None else mask.stride(0),
+                                _p(gx), K, _precision, _st()), "linear_bwd_x")
+    return gx
+
+
+def _linear_bwd_w(gy, x, want_bias=True):
+    M, N = gy.shape
+    K = x.shape[1]
+    gw = torch.empty(N, K, dtype=torch.float32, device=gy.device)
+    gb = torch.empty(N, dtype=torch.float32, device=gy.device) if want_bias else None
+    check(lib.pgnn_linear_bwd_w(_p(gy), gy.stride(0), _p(x), x.stride(0), M, N, K, _p(gw), _p(gb), _precision, _st()),
+          "linear_bwd_w")
+    return gw, gb
+
+
+class _Linear(Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _dev(x, w, b)
+        x, w = _f32(x), _f32(w).contiguous()
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return _linear_fwd(x, w, b, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _f32(g)
+        gx = _linear_bwd_x(g, w) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = _linear_bwd_w(g, x, ctx.has_bias)
+        return gx, gw, gb
+
+
+def linear(x, w, b=None):
+    return _Linear.apply(x, w, b)
+
+
+class _Mlp2(Function):
+    """Linear -> ReLU -> Linear (GINConv.mlp, chem/model.py:29): the hidden activation doubles as the ReLU mask."""
+
+    @staticmethod
+    def forward(ctx, a, w1, b1, w2, b2):
+        _dev(a, w1, b1, w2, b2)
+        a, w1, w2 = _f32(a), _f32(w1).contiguous(), _f32(w2).contiguous()
+        z1 = _linear_fwd(a, w1, b1, True)
+        z2 = _linear_fwd(z1, w2, b2, False)
+        ctx.save_for_backward(a, w1, w2, z1)
+        return z2
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w1, w2, z1 = ctx.saved_tensors
+        g = _f32(g)
+        gw2, gb2 = _linear_bwd_w(g, z1)
+        gz1 = _linear_bwd_x(g, w2, mask=z1)
+        gw1, gb1 = _linear_bwd_w(gz1, a)
+        ga = _linear_bwd_x(gz1, w1) if ctx.needs_input_grad[0] else None
+        return ga, gw1, gb1, gw2, gb2
+
+
+def mlp2(a, w1, b1, w2, b2):
+    return _Mlp2.apply(a, w1, b1, w2, b2)
+
+
+class _BatchNorm(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, relu, momentum, eps):
+        _dev(x, gamma, beta)
+        x = _f32(x)
+        M, C = x.shape
+        y = torch.empty(M, C, dtype=torch.float32, device=x.device)
+        if training:
+            if M == 0:
+                raise PgnnError("BatchNorm in training mode needs at least one row")
+            mean = torch.empty(C, dtype=torch.float32, device=x.device)
+            invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            wsb = lib.pgnn_bn_workspace_bytes(M, C)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+            check(lib.pgnn_bn_fwd_train(_p(x), x.stride(0), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                        _p(nbt), float(momentum), float(eps), int(relu), _p(y), C, _p(mean), _p(invstd),
+                                        None, None, _p(ws), wsb, _st()), "bn_fwd_train")
+            ctx.save_for_backward(x, gamma, beta, mean, invstd)
+        else:
+            check(lib.pgnn_bn_fwd_eval(_p(x), x.stride(0), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                       float(eps), int(relu), _p(y), C, _st()), "bn_fwd_eval")
+        ctx.training, ctx.relu = training, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.training:
+            raise PgnnError("backward through eval-mode BatchNorm is not implemented (no in-scope caller trains with "
+                            "model.eval(); SURVEY.md section 3.3)")
+        x, gamma, beta, mean, invstd = ctx.saved_tensors
+        g = _f32(g)
+        M, C = x.shape
+        gx = torch.empty(M, C, dtype=torch.float32, device=g.device)
+        gg = torch.empty(C, dtype=torch.float32, device=g.device)
+        gb = torch.empty(C, dtype=torch.float32, device=g.device)
+        wsb = lib.pgnn_bn_workspace_bytes(M, C)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=g.device)
+        check(lib.pgnn_bn_bwd(_p(g), g.stride(0), _p(x), x.stride(0), M, C, _p(gamma), _p(beta), _p(mean), _p(invstd),
+                              int(ctx.relu), _p(gx), C, _p(gg), _p(gb), _p(ws), wsb, _st()), "bn_bwd")
+        return gx, gg, gb, None, None, None, None, None, None, None
+
+
+def batch_norm(x, bn: torch.nn.BatchNorm1d, relu: bool):
+    """Apply a torch.nn.BatchNorm1d module's parameters/buffers with the library kernels (+ fused ReLU)."""
+    training = bn.training or bn.running_mean is None
+    return _BatchNorm.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                            bn.num_batches_tracked if training else None, training, relu,
+                            0.1 if bn.momentum is None else bn.momentum, bn.eps)
+
+
+class _Relu(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _dev(x)
+        x = _f32(x)
+        y = torch.empty_like(x, memory_format=torch.contiguous_format)
+        check(lib.pgnn_relu_fwd(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(y), y.stride(0), _st()), "relu_fwd")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _f32(g)
+        gx = torch.empty_like(y)
+        check(lib.pgnn_relu_bwd(_p(g), g.stride(0), _p(y), y.stride(0), y.shape[0], y.shape[1], _p(gx), gx.stride(0), _st()),
+              "relu_bwd")
+        return gx
+
+
+def relu(x):
+    return _Relu.apply(x)
+
+
+class _L2Norm(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _dev(x)
+        x = _f32(x)
+        y = torch.empty_like(x, memory_format=torch.contiguous_format)
+        nrm = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        check(lib.pgnn_l2norm_fwd(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(y), y.stride(0), _p(nrm), _st()), "l2norm_fwd")
+        ctx.save_for_backward(y, nrm)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, nrm = ctx.saved_tensors
+        g = _f32(g)
+        gx = torch.empty_like(y)
+        check(lib.pgnn_l2norm_bwd(_p(g), g.stride(0), _p(y), y.stride(0), _p(nrm), y.shape[0], y.shape[1], _p(gx),
+                                  gx.stride(0), _st()), "l2norm_bwd")
+        return gx
+
+
+def l2_normalize(x):
+    return _L2Norm.apply(x)
+
+
+class _ChemEmbed(Function):
+    @staticmethod
+    def forward(ctx, x, t1, t2):
+        _dev(x, t1, t2)
+        if x.dtype != torch.int64 or x.dim() != 2 or x.shape[1] != 2:
+            raise PgnnError("chem node features must be int64 [N, 2]")
+        x, t1, t2 = x.contiguous(), _f32(t1).contiguous(), _f32(t2).contiguous()
+        n, C = x.shape[0], t1.shape[1]
+        out = torch.empty(n, C, dtype=torch.float32, device=x.device)
+        check(lib.pgnn_chem_embed_fwd(_p(x), _p(t1), _p(t2), n, C, _p(out), C, _st()), "chem_embed_fwd")
+        ctx.x, ctx.shapes = x, (t1.shape[0], t2.shape[0], C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        r1, r2, C = ctx.shapes
+        g1 = torch.empty(r1, C, dtype=torch.float32, device=g.device)
+        g2 = torch.empty(r2, C, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_chem_embed_bwd(_p(ctx.x), _p(g), g.stride(0), ctx.x.shape[0], C, _p(g1), r1, _p(g2), r2, _st()),
+              "chem_embed_bwd")
+        return None, g1, g2
+
+
+def chem_embed(x, t1, t2):
+    return _ChemEmbed.apply(x, t1, t2)
+
+
+class _BioEmbed(Function):
+    @staticmethod
+    def forward(ctx, x, tab):
+        _dev(x, tab)
+        xv = x.reshape(-1)
+        if xv.dtype != torch.float32:
+            xv = xv.to(torch.float32)
+        xv, tab = xv.contiguous(), _f32(tab).contiguous()
+        n, C = xv.shape[0], tab.shape[1]
+        out = torch.empty(n, C, dtype=torch.float32, device=tab.device)
+        check(lib.pgnn_bio_embed_fwd(_p(xv), _p(tab), n, C, _p(out), C, _st()), "bio_embed_fwd")
+        ctx.xv, ctx.C = xv, C
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        gt = torch.empty(2, ctx.C, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_bio_embed_bwd(_p(ctx.xv), _p(g), g.stride(0), ctx.xv.shape[0], ctx.C, _p(gt), _st()), "bio_embed_bwd")
+        return None, gt
+
+
+def bio_embed(x, tab):
+    return _BioEmbed.apply(x, tab)
+
+
+class _SegmentMean(Function):
+    @staticmethod
+    def forward(ctx, x, segs):
+        _dev(x)
+        x = _f32(x)
+        C = x.shape[1]
+        out = torch.empty(segs.num_seg, C, dtype=torch.float32, device=x.device)
+        check(lib.pgnn_segment_mean_fwd(_p(x), x.stride(0), _p(segs.ptr), _p(segs.order), segs.num_seg, C, _p(out), C, _st()),
+              "segment_mean_fwd")
+        ctx.segs, ctx.C = segs, C
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        s = ctx.segs
+        gx = torch.empty(s.n, ctx.C, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_segment_mean_bwd(_p(g), g.stride(0), _p(s.seg), _p(s.ptr), s.n, ctx.C, _p(gx), ctx.C, _st()),
+              "segment_mean_bwd")
+        return gx, None
+
+
+def global_mean_pool(x, batch, size=None):
+    """torch_geometric.nn.global_mean_pool replacement (chem/model.py:326): scatter_mean over `batch`."""
+    if size is None:
+        size = int(batch.max().item()) + 1 if batch.numel() else 0  # same D2H sync PyG 1.0.3 performs
+    return _SegmentMean.apply(x, Segments(batch, size))
+
+
+def segment_mean(x, segs: Segments):
+    return _SegmentMean.apply(x, segs)
+
+
+class _RowGather(Function):
+    @staticmethod
+    def forward(ctx, x, idx, idx2):
+        _dev(x, idx, idx2)
+        x = _f32(x)
+        idx = idx.contiguous()
+        idx2 = None if idx2 is None else idx2.contiguous()
+        if idx.dtype != torch.int64 or (idx2 is not None and idx2.dtype != torch.int64):
+            raise PgnnError("gather indices must be int64")
+        m, C = idx.shape[0], x.shape[1]
+        out = torch.empty(m, C, dtype=torch.float32, device=x.device)
+        check(lib.pgnn_row_gather_fwd(_p(x), x.stride(0), _p(idx), _p(idx2), m, C, _p(out), C, _st()), "row_gather_fwd")
+        ctx.idx, ctx.idx2, ctx.shape = idx, idx2, tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32(g)
+        n, C = ctx.shape
+        gx = torch.zeros(n, C, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_row_gather_bwd(_p(g), g.stride(0), _p(ctx.idx), _p(ctx.idx2), ctx.idx.shape[0], C, _p(gx), C, _st()),
+              "row_gather_bwd")
+        return gx, None, None
+
+
+def row_gather(x, idx, idx2=None):
+    """x[idx] (+ x[idx2]): node_rep[masked_atom_indices], rep[u]+rep[v], node_rep[center_node_idx]."""
+    return _RowGather.apply(x, idx, idx2)
+
+
+class _ShiftedRowDot(Function):
+    @staticmethod
+    def forward(ctx, a, b, shift):
+        _dev(a, b)
+        a, b = _f32(a), _f32(b)
+        B, C = a.shape
+        out = torch.empty(B, dtype=torch.float32, device=a.device)
+        check(lib.pgnn_shifted_rowdot_fwd(_p(a), a.stride(0), _p(b), b.stride(0), B, C, shift, _p(out), _st()),
+              "shifted_rowdot_fwd")
+        ctx.save_for_backward(a, b)
+        ctx.shift = shift
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        B, C = a.shape
+        ga, gb = torch.empty(B, C, dtype=torch.float32, device=g.device), torch.empty(B, C, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_shifted_rowdot_bwd(_p(g), _p(a), a.stride(0), _p(b), b.stride(0), B, C, ctx.shift, 0, _p(ga), C,
+                                          _p(gb), C, _st()), "shifted_rowdot_bwd")
+        return ga, gb, None
+
+
+def shifted_rowdot(a, b, shift=0):
+    """sum(a * b[cycle_index(B, shift)], dim=1) (chem/pretrain_contextpred.py:36-39,66-67); shift 0 = positives."""
+    return _ShiftedRowDot.apply(a, b, int(shift))

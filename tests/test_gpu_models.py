@@ -1,0 +1,192 @@
+"""GPU: the drop-in modules end to end against the oracle and against the golden vectors frozen from the
+reference's own model.py (tests/golden/make_golden.py)."""
+import importlib
+import types
+
+import pytest
+import torch
+
+from oracle import gnn_oracle as O
+from golden_util import TYPES, check_against_golden, golden_batch, golden_params, load, probe
+
+pytestmark = pytest.mark.gpu
+syn = importlib.import_module("pretrain-gnns_b200.synthetic")
+chem = importlib.import_module("pretrain-gnns_b200.chem.model")
+bio = importlib.import_module("pretrain-gnns_b200.bio.model")
+ops = importlib.import_module("pretrain-gnns_b200.ops")
+DEV = "cuda:0"
+IMPLEMENTED = [t for t in TYPES if t != "gat" or hasattr(ops, "gat")]
+
+
+def _dev(b):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
+
+
+def _run(domain, t, b, P, training):
+    mod = chem if domain == "chem" else bio
+    model = mod.GNN(5, 300, JK="last", drop_ratio=0, gnn_type=t)
+    model.load_state_dict(P)
+    model.to(DEV).train(training)
+    d = _dev(b)
+    out = model(d["x"], d["edge_index"], d["edge_attr"])
+    return model, out
+
+
+@pytest.mark.parametrize("domain", ["chem", "bio"])
+@pytest.mark.parametrize("t", IMPLEMENTED)
+def test_module_matches_reference_golden(domain, t):
+    G = load(domain, t)
+    b, P = golden_batch(domain), golden_params(domain, t)
+    with torch.no_grad():
+        _, out_eval = _run(domain, t, b, P, False)
+    model, out_train = _run(domain, t, b, P, True)
+    (out_train * probe(out_train.shape, 99).to(DEV)).sum().backward()
+    grads = {k: p.grad.cpu() for k, p in model.named_parameters()}
+    stats = {k: v.cpu() for k, v in model.state_dict().items()}
+    bad = check_against_golden(G, out_eval.cpu(), out_train.detach().cpu(), grads, stats)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("t", IMPLEMENTED)
+def test_chem_encoder_vs_oracle_b32(t):
+    """BASELINE configs[0]: 32 ZINC-shaped molecules, eval-mode forward (plus a train-mode fwd+bwd)."""
+    b = syn.zinc_batch(32, 100)
+    P = O.make_params("chem", t, 5, 300, seed=21)
+    with torch.no_grad():
+        ref = O.chem_gnn(P, b["x"], b["edge_index"], b["edge_attr"], 5, t, False)
+        _, out = _run("chem", t, b, P, False)
+    err = (out.cpu() - ref).abs()
+    assert bool((err <= 1e-4 + 1e-4 * ref.abs()).all()), err.max()
+    L = O.leaf_params(P)
+    ref_t = O.chem_gnn(L, b["x"], b["edge_index"], b["edge_attr"], 5, t, True)
+    R = probe(ref_t.shape, 5)
+    (ref_t * R).sum().backward()
+    model, out_t = _run("chem", t, b, P, True)
+    (out_t * R.to(DEV)).sum().backward()
+    err = (out_t.detach().cpu() - ref_t.detach()).abs()
+    assert bool((err <= 1e-4 + 1e-4 * ref_t.detach().abs()).all()), err.max()
+    gscale = sorted(float(v.grad.abs().max()) for v in L.values() if v.requires_grad)
+    floor = max(gscale[len(gscale) // 2], 1.0)
+    for k, p in model.named_parameters():
+        e = (p.grad.cpu() - L[k].grad).abs().max().item() / max(L[k].grad.abs().max().item(), floor)
+        assert e < 2e-4, (k, e)
+
+
+def test_chem_graphpred_and_masking_heads():
+    b = syn.mask_atoms(syn.zinc_batch(32, 7), 7, mask_edge=True)
+    P = O.make_params("chem", "gin", 5, 300, seed=3)
+    g = torch.Generator().manual_seed(1)
+    Wg, bg = torch.randn(12, 300, generator=g) * 0.05, torch.randn(12, generator=g) * 0.05
+    Wa, ba = torch.randn(119, 300, generator=g) * 0.05, torch.randn(119, generator=g) * 0.05
+    full = {"gnn." + k: v for k, v in P.items()}
+    full.update({"graph_pred_linear.weight": Wg, "graph_pred_linear.bias": bg})
+    ref = O.chem_graphpred(full, b["x"], b["edge_index"], b["edge_attr"], b["batch"], 32, 5, "gin", False)
+    model = chem.GNN_graphpred(5, 300, 12)
+    model.load_state_dict(full)
+    model.to(DEV).eval()
+    d = _dev(b)
+    with torch.no_grad():
+        out = model(d["x"], d["edge_index"], d["edge_attr"], d["batch"])
+        data = types.SimpleNamespace(**{k: d[k] for k in ("x", "edge_index", "edge_attr", "batch")})
+        out2 = model(data)
+    assert torch.allclose(out.cpu(), ref, atol=1e-4, rtol=1e-4) and torch.equal(out, out2)
+    # masking heads (chem/pretrain_masking.py:51-61) on top of the train-mode encoder
+    L = O.leaf_params(P)
+    rep_ref = O.chem_gnn(L, b["x"], b["edge_index"], b["edge_attr"], 5, "gin", True)
+    loss_ref, logits_ref = O.masking_loss(rep_ref, b["masked_atom_indices"], b["mask_node_label"][:, 0], Wa, ba)
+    enc = chem.GNN(5, 300)
+    enc.load_state_dict(P)
+    enc.to(DEV).train()
+    rep = enc(d["x"], d["edge_index"], d["edge_attr"])
+    logits = ops.linear(ops.row_gather(rep, d["masked_atom_indices"]), Wa.to(DEV), ba.to(DEV))
+    loss = torch.nn.functional.cross_entropy(logits.double(), d["mask_node_label"][:, 0])
+    assert torch.allclose(logits.detach().cpu(), logits_ref.detach(), atol=1e-4, rtol=1e-4)
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    me = d["edge_index"][:, d["connected_edge_indices"]]
+    bond = ops.row_gather(rep, me[0].contiguous(), me[1].contiguous())
+    mer = b["edge_index"][:, b["connected_edge_indices"]]
+    assert torch.allclose(bond.detach().cpu(), (rep_ref[mer[0]] + rep_ref[mer[1]]).detach(), atol=1e-4, rtol=1e-4)
+
+
+def test_contextpred_step_vs_oracle():
+    """chem/pretrain_contextpred.py:54-93 with a 5-layer substructure and a 3-layer context encoder."""
+    b = syn.substruct_context_batch(16, 4)
+    Ps, Pc = O.make_params("chem", "gin", 5, 300, seed=1), O.make_params("chem", "gin", 3, 300, seed=2)
+    Ls, Lc = O.leaf_params(Ps), O.leaf_params(Pc)
+    sub = O.chem_gnn(Ls, b["x_substruct"], b["edge_index_substruct"], b["edge_attr_substruct"], 5, "gin", True)[b["center_substruct_idx"]]
+    ov = O.chem_gnn(Lc, b["x_context"], b["edge_index_context"], b["edge_attr_context"], 3, "gin", True)[b["overlap_context_substruct_idx"]]
+    pos_r, neg_r = O.contextpred_scores(sub, ov, b["batch_overlapped_context"], 16, 1)
+    O.contextpred_loss(pos_r, neg_r).backward()
+    ms, mc = chem.GNN(5, 300), chem.GNN(3, 300)
+    ms.load_state_dict(Ps); mc.load_state_dict(Pc)
+    ms.to(DEV).train(); mc.to(DEV).train()
+    d = _dev(b)
+    s = ops.row_gather(ms(d["x_substruct"], d["edge_index_substruct"], d["edge_attr_substruct"]), d["center_substruct_idx"])
+    o = ops.row_gather(mc(d["x_context"], d["edge_index_context"], d["edge_attr_context"]), d["overlap_context_substruct_idx"])
+    ctx = ops.global_mean_pool(o, d["batch_overlapped_context"], 16)
+    pos, neg = ops.shifted_rowdot(s, ctx, 0), ops.shifted_rowdot(s, ctx, 1)
+    O.contextpred_loss(pos, neg).backward()
+    assert torch.allclose(pos.detach().cpu(), pos_r.detach(), atol=2e-4, rtol=1e-4)
+    assert torch.allclose(neg.detach().cpu(), neg_r.detach(), atol=2e-4, rtol=1e-4)
+    for model, L in ((ms, Ls), (mc, Lc)):
+        for k, p in model.named_parameters():
+            ref = L[k].grad
+            e = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2)
+            assert e < 5e-4, (k, e)
+
+
+def test_bio_graphpred_vs_oracle():
+    b = syn.ppi_batch(3, 8, n_lo=60, n_hi=90, num_tasks=40)
+    P = O.make_params("bio", "gin", 5, 300, seed=4)
+    g = torch.Generator().manual_seed(2)
+    full = {"gnn." + k: v for k, v in P.items()}
+    full["graph_pred_linear.weight"] = torch.randn(40, 600, generator=g) * 0.03
+    full["graph_pred_linear.bias"] = torch.randn(40, generator=g) * 0.03
+    L = O.leaf_params(full)
+    ref = O.bio_graphpred(L, b["x"], b["edge_index"], b["edge_attr"], b["batch"], b["center_node_idx"], 3, 5, "gin", True)
+    y = b["go_target_pretrain"].view(3, 40).double()
+    torch.nn.functional.binary_cross_entropy_with_logits(ref.double(), y).backward()
+    model = bio.GNN_graphpred(5, 300, 40)
+    model.load_state_dict(full)
+    model.to(DEV).train()
+    d = types.SimpleNamespace(**_dev(b))
+    out = model(d)
+    torch.nn.functional.binary_cross_entropy_with_logits(out.double(), y.to(DEV)).backward()
+    assert torch.allclose(out.detach().cpu(), ref.detach(), atol=1e-4, rtol=1e-4)
+    for k, p in model.named_parameters():
+        r = L[k].grad
+        e = (p.grad.cpu() - r).abs().max().item() / max(r.abs().max().item(), 1e-3)
+        assert e < 5e-4, (k, e)
+
+
+def test_full_size_properties_b256():
+    """BASELINE configs[1] size (B=256): size-independent properties instead of an oracle run.
+    (1) determinism: two runs give identical bits; (2) permutation equivariance: relabelling the nodes of
+    the batch permutes the output rows; (3) graph independence in eval mode: a graph's rows do not change
+    when the other 255 graphs are dropped."""
+    b = syn.zinc_batch(256, 42)
+    P = O.make_params("chem", "gin", 5, 300, seed=9)
+    with torch.no_grad():
+        _, o1 = _run("chem", "gin", b, P, False)
+        _, o2 = _run("chem", "gin", b, P, False)
+        assert torch.equal(o1, o2)
+        n = b["x"].shape[0]
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(0))
+        inv = torch.empty_like(perm); inv[perm] = torch.arange(n)
+        bp = dict(b); bp["x"] = b["x"][perm]; bp["edge_index"] = inv[b["edge_index"]]
+        _, o3 = _run("chem", "gin", bp, P, False)
+        assert torch.allclose(o3, o1[perm.to(DEV)], atol=1e-5, rtol=1e-5)
+        n0 = int(b["ptr"][1])
+        e0 = int((b["edge_index"][0] < n0).sum())
+        b0 = dict(x=b["x"][:n0], edge_index=b["edge_index"][:, :e0], edge_attr=b["edge_attr"][:e0])
+        _, o4 = _run("chem", "gin", b0, P, False)
+        assert torch.allclose(o4, o1[:n0], atol=1e-5, rtol=1e-5)
+
+
+def test_value_errors_match_reference():
+    with pytest.raises(ValueError):
+        chem.GNN(1, 300)
+    with pytest.raises(ValueError):
+        chem.GNN(5, 300)(1, 2)
+    with pytest.raises(ValueError):
+        chem.GNN_graphpred(5, 300, 1, graph_pooling="bogus")
