@@ -181,19 +181,21 @@ PGNN_API int pgnn_l2norm_bwd(const float* gy, int64_t ldgy, const float* y, int6
  * xl [N,H*D] is weight_linear(x).  Edge embedding rows e_k [H*D] are  Tsel = T rows selected/combined
  * by the per-edge features: chem e_k = T[a0_k] + T[6 + a1_k] (T [9,H*D]); bio e_k = sum_q attr[k,q] T[q] +
  * T[9] (T [10,H*D] = [W^T ; b]).  `feat` is the raw edge_attr (int64 [E,2] for chem, float [E,9] for bio).
- * alpha [E+N, H] (bucket order per target then self-loop at E+i) is written for backward.
+ * alpha [E+N, H] (target-bucket order, then the self-loop of node i at E+i) and pq [N,H,2] (the per-node
+ * halves <att_i, xl_n> and <att_j, xl_n> of the attention logit) are written for backward.  D <= 320.
  * ------------------------------------------------------------------------------------------- */
 PGNN_API int pgnn_gat_fwd(const float* xl, int64_t num_nodes, int64_t H, int64_t D, const float* att /*[H,2D]*/,
                           const float* T, int is_bio, const void* feat, const int32_t* rowptr_t,
                           const int32_t* nbr_t, const int32_t* eid_t, int64_t num_edges, const float* bias /*[D]*/,
-                          float slope, float* alpha, float* out /*[N,D]*/, int64_t ldo, void* stream);
+                          float slope, float* alpha, float* pq, float* out /*[N,D]*/, int64_t ldo, void* stream);
 PGNN_API int64_t pgnn_gat_bwd_workspace_bytes(int64_t num_nodes, int64_t num_edges, int64_t H, int64_t D);
+/* gxl [N,H*D], gatt [H,2D], gT [Q,H*D] (Q = 9 chem / 10 bio), gbias [D]: all OVERWRITTEN */
 PGNN_API int pgnn_gat_bwd(const float* g /*[N,D]*/, int64_t ldg, const float* xl, int64_t num_nodes, int64_t H,
                           int64_t D, const float* att, const float* T, int is_bio, const void* feat,
                           const int32_t* rowptr_t, const int32_t* nbr_t, const int32_t* eid_t,
                           const int32_t* rowptr_s, const int32_t* nbr_s, const int32_t* eid_s,
-                          int64_t num_edges, float slope, const float* alpha,
-                          float* gxl /*[N,H*D]*/, float* gatt /*[H,2D]*/, float* gT, float* gbias /*[D]*/,
+                          int64_t num_edges, float slope, const float* alpha, const float* pq,
+                          float* gxl, float* gatt, float* gT, float* gbias,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

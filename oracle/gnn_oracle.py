@@ -44,7 +44,7 @@ def chem_edge_rows(P, pre, edge_attr, n):
     loops = torch.zeros(n, 2, dtype=edge_attr.dtype)
     loops[:, 0] = SELF_LOOP_BOND
     ea = torch.cat([edge_attr, loops], dim=0)
-    return P[pre + "edge_embedding1.weight"][ea[:, 0]] + P[pre + "edge_embedding2.weight"][ea[:, 1]]
+    return F.embedding(ea[:, 0], P[pre + "edge_embedding1.weight"]) + F.embedding(ea[:, 1], P[pre + "edge_embedding2.weight"])
 
 
 def bio_edge_rows(P, pre, edge_attr, n):
@@ -83,23 +83,20 @@ def segment_softmax(alpha, target, n):
 
 
 def batch_norm(P, pre, h, training, new_stats=None):
-    """torch.nn.BatchNorm1d (chem/model.py:269, bio/model.py:24). Train: batch mean / biased var;
-    running stats updated with momentum 0.1 and the unbiased variance."""
+    """torch.nn.BatchNorm1d (chem/model.py:269, bio/model.py:24) through the same functional the module
+    calls.  Train: batch mean / biased var; running stats (momentum 0.1, unbiased var) are returned in
+    `new_stats` instead of being updated in place, so the parameter dictionary stays immutable."""
     w, b = P[pre + "weight"], P[pre + "bias"]
-    if training:
-        mean = h.mean(0)
-        var = h.var(0, unbiased=False)
-        if new_stats is not None:
-            n = h.shape[0]
-            with torch.no_grad():
-                new_stats[pre + "running_mean"] = (1 - BN_MOMENTUM) * P[pre + "running_mean"] + BN_MOMENTUM * mean
-                new_stats[pre + "running_var"] = (1 - BN_MOMENTUM) * P[pre + "running_var"] + \
-                    BN_MOMENTUM * var * (n / max(n - 1, 1))
-                if pre + "num_batches_tracked" in P:
-                    new_stats[pre + "num_batches_tracked"] = P[pre + "num_batches_tracked"] + 1
-    else:
-        mean, var = P[pre + "running_mean"], P[pre + "running_var"]
-    return (h - mean) / torch.sqrt(var + BN_EPS) * w + b
+    rm, rv = P[pre + "running_mean"].detach(), P[pre + "running_var"].detach()
+    if not training:
+        return F.batch_norm(h, rm, rv, w, b, False, BN_MOMENTUM, BN_EPS)
+    rm, rv = rm.clone(), rv.clone()
+    y = F.batch_norm(h, rm, rv, w, b, True, BN_MOMENTUM, BN_EPS)
+    if new_stats is not None:
+        new_stats[pre + "running_mean"], new_stats[pre + "running_var"] = rm, rv
+        if pre + "num_batches_tracked" in P:
+            new_stats[pre + "num_batches_tracked"] = P[pre + "num_batches_tracked"] + 1
+    return y
 
 
 # --------------------------------------------------------------------------------------------
@@ -107,14 +104,14 @@ def batch_norm(P, pre, h, training, new_stats=None):
 # --------------------------------------------------------------------------------------------
 def gin_conv_chem(P, pre, h, ei, edge_rows):
     """chem/model.py:37-55: aggr = sum(x_j + e); out = W2 relu(W1 aggr + b1) + b2."""
-    aggr = reduce_onto_target(h[ei[1]] + edge_rows, ei[0], h.shape[0])
+    aggr = reduce_onto_target(h.index_select(0, ei[1]) + edge_rows, ei[0], h.shape[0])
     z = F.relu(F.linear(aggr, P[pre + "mlp.0.weight"], P[pre + "mlp.0.bias"]))
     return F.linear(z, P[pre + "mlp.2.weight"], P[pre + "mlp.2.bias"])
 
 
 def gin_conv_bio(P, pre, h, ei, edge_rows, training, new_stats=None):
     """bio/model.py:37-58: message = cat([x_j, e]); MLP = Linear(2D,2D) BN ReLU Linear(2D,D)."""
-    aggr = reduce_onto_target(torch.cat([h[ei[1]], edge_rows], dim=1), ei[0], h.shape[0])
+    aggr = reduce_onto_target(torch.cat([h.index_select(0, ei[1]), edge_rows], dim=1), ei[0], h.shape[0])
     z = F.linear(aggr, P[pre + "mlp.0.weight"], P[pre + "mlp.0.bias"])
     z = F.relu(batch_norm(P, pre + "mlp.1.", z, training, new_stats))
     return F.linear(z, P[pre + "mlp.3.weight"], P[pre + "mlp.3.bias"])
@@ -124,13 +121,13 @@ def gcn_conv(P, pre, h, ei, edge_rows):
     """chem/model.py:85-104, bio/model.py:92-114: Linear first, then sum(norm * (x_j + e))."""
     norm = gcn_norm(ei, h.shape[0], h.dtype)
     x = F.linear(h, P[pre + "linear.weight"], P[pre + "linear.bias"])
-    return reduce_onto_target(norm.view(-1, 1) * (x[ei[1]] + edge_rows), ei[0], h.shape[0])
+    return reduce_onto_target(norm.view(-1, 1) * (x.index_select(0, ei[1]) + edge_rows), ei[0], h.shape[0])
 
 
 def sage_conv(P, pre, h, ei, edge_rows):
     """chem/model.py:182-202, bio/model.py:201-224: Linear, mean(x_j + e), L2-normalise rows."""
     x = F.linear(h, P[pre + "linear.weight"], P[pre + "linear.bias"])
-    aggr = reduce_onto_target(x[ei[1]] + edge_rows, ei[0], h.shape[0], mean=True)
+    aggr = reduce_onto_target(x.index_select(0, ei[1]) + edge_rows, ei[0], h.shape[0], mean=True)
     return F.normalize(aggr, p=2, dim=-1)
 
 
@@ -139,8 +136,8 @@ def gat_conv(P, pre, h, ei, edge_rows, heads=2):
     leaky_relu(<[x_i, x_j], att>)); out = mean_heads(sum x_j * alpha) + bias."""
     n, d = h.shape[0], P[pre + "bias"].shape[0]
     x = F.linear(h, P[pre + "weight_linear.weight"], P[pre + "weight_linear.bias"]).view(n, heads, d)
-    xj = x[ei[1]] + edge_rows.view(-1, heads, d)
-    xi = x[ei[0]]
+    xj = x.index_select(0, ei[1]) + edge_rows.view(-1, heads, d)
+    xi = x.index_select(0, ei[0])
     alpha = (torch.cat([xi, xj], dim=-1) * P[pre + "att"]).sum(-1)
     alpha = segment_softmax(F.leaky_relu(alpha, GAT_SLOPE), ei[0], n)
     out = reduce_onto_target(xj * alpha.view(-1, heads, 1), ei[0], n)
@@ -154,7 +151,7 @@ def chem_gnn(P, x, edge_index, edge_attr, num_layer, gnn_type="gin", training=Fa
              pre="", keep=None):
     """chem/model.py:255-290 with JK='last', drop_ratio=0."""
     n = x.shape[0]
-    h = P[pre + "x_embedding1.weight"][x[:, 0]] + P[pre + "x_embedding2.weight"][x[:, 1]]
+    h = F.embedding(x[:, 0], P[pre + "x_embedding1.weight"]) + F.embedding(x[:, 1], P[pre + "x_embedding2.weight"])
     ei = with_self_loops(edge_index, n)
     for l in range(num_layer):
         lp = f"{pre}gnns.{l}."
@@ -186,7 +183,7 @@ def bio_gnn(P, x, edge_index, edge_attr, num_layer, gnn_type="gin", training=Fal
         lp = f"{pre}gnns.{l}."
         rows = bio_edge_rows(P, lp, edge_attr, n)
         if l == 0:
-            h = P[lp + "input_node_embeddings.weight"][h.to(torch.int64).view(-1)]  # bio/model.py:49-50
+            h = F.embedding(h.to(torch.int64).view(-1), P[lp + "input_node_embeddings.weight"])  # bio/model.py:49-50
         if gnn_type == "gin":
             h = gin_conv_bio(P, lp, h, ei, rows, training, new_stats)
         elif gnn_type == "gcn":
@@ -332,7 +329,9 @@ def leaf_params(P, dtype=None):
     """Clone into autograd leaves (trainable entries only)."""
     out = {}
     for k, v in P.items():
-        v = v.clone() if dtype is None or not v.is_floating_point() else v.to(dtype)
+        v = v.detach().clone()
+        if dtype is not None and v.is_floating_point():
+            v = v.to(dtype)
         if is_float_param(k, v):
             v.requires_grad_(True)
         out[k] = v

@@ -149,7 +149,7 @@ constexpr int kTblRows = 128;
 constexpr int kMaxQ = 16;
 __global__ void __launch_bounds__(128)
 k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g, int64_t ldg, int64_t g_off, int64_t n,
-                 int C, float* __restrict__ gT) {
+                 int C, float* __restrict__ gT, int64_t ldt) {
   __shared__ float s_S[kTblRows * kMaxQ];
   const int64_t r0 = (int64_t)blockIdx.x * kTblRows;
   const int rows = (int)((n - r0) < kTblRows ? (n - r0) : kTblRows);
@@ -168,7 +168,7 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
   }
 #pragma unroll
   for (int q = 0; q < kMaxQ; ++q)
-    if (q < Q) atomicAdd(&gT[(int64_t)q * C + c], acc[q]);
+    if (q < Q) atomicAdd(&gT[(int64_t)q * ldt + c], acc[q]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -235,6 +235,16 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+// shared with gat.cu: gT[q*ldt + c] += sum_i S[i][q] g[i][g_off + c]  (caller zeroes gT)
+int pgnn_internal_edge_table_bwd(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
+                                 int64_t ldt, cudaStream_t st) {
+  if (n == 0) return PGNN_OK;
+  dim3 grid((unsigned)ceil_div(n, kTblRows), (unsigned)ceil_div(C, 128));
+  k_edge_table_bwd<<<grid, 128, 0, st>>>(S, Q, g, ldg, g_off, n, C, gT, ldt);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
 extern "C" {
 
 int pgnn_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
@@ -278,10 +288,7 @@ int pgnn_edge_table_bwd(const float* S, int64_t Q, const float* g, int64_t ldg, 
   PGNN_CUDA(cudaMemsetAsync(gT, 0, sizeof(float) * Q * C, st));
   if (num_nodes == 0) return PGNN_OK;
   PGNN_CHECK_ARG(S && g);
-  dim3 grid((unsigned)ceil_div(num_nodes, kTblRows), (unsigned)ceil_div(C, 128));
-  k_edge_table_bwd<<<grid, 128, 0, st>>>(S, (int)Q, g, ldg, g_off, num_nodes, (int)C, gT);
-  PGNN_LAUNCH_CHECK();
-  return PGNN_OK;
+  return pgnn_internal_edge_table_bwd(S, (int)Q, g, ldg, g_off, num_nodes, (int)C, gT, C, st);
 }
 
 int pgnn_chem_embed_fwd(const int64_t* x, const float* tab1, const float* tab2, int64_t num_nodes, int64_t C, float* out,

@@ -510,3 +510,46 @@ class _ShiftedRowDot(Function):
 def shifted_rowdot(a, b, shift=0):
     """sum(a * b[cycle_index(B, shift)], dim=1) (chem/pretrain_contextpred.py:36-39,66-67); shift 0 = positives."""
     return _ShiftedRowDot.apply(a, b, int(shift))
+
+
+class _Gat(Function):
+    @staticmethod
+    def forward(ctx, xl, att, T, bias, edge_attr, graph, heads, slope, is_bio):
+        _dev(xl, att, T, bias, edge_attr)
+        xl, att, T, bias = _f32(xl).contiguous(), _f32(att).contiguous(), _f32(T).contiguous(), _f32(bias).contiguous()
+        ea = edge_attr.contiguous()
+        want = torch.float32 if is_bio else torch.int64
+        if ea.dtype != want or ea.shape != (graph.e, 9 if is_bio else 2):
+            raise PgnnError("edge_attr has the wrong dtype/shape for %s GAT" % ("bio" if is_bio else "chem"))
+        n, H = graph.n, int(heads)
+        D = xl.shape[1] // H
+        alpha = torch.empty(graph.e + n, H, dtype=torch.float32, device=xl.device)
+        pq = torch.empty(n, H, 2, dtype=torch.float32, device=xl.device)
+        out = torch.empty(n, D, dtype=torch.float32, device=xl.device)
+        check(lib.pgnn_gat_fwd(_p(xl), n, H, D, _p(att), _p(T), int(is_bio), _p(ea), _p(graph.rowptr_t), _p(graph.nbr_t),
+                               _p(graph.eid_t), graph.e, _p(bias), float(slope), _p(alpha), _p(pq), _p(out), D, _st()), "gat_fwd")
+        ctx.save_for_backward(xl, att, T, alpha, pq, ea)
+        ctx.graph, ctx.H, ctx.D, ctx.slope, ctx.is_bio, ctx.att_shape = graph, H, D, float(slope), bool(is_bio), att.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xl, att, T, alpha, pq, ea = ctx.saved_tensors
+        g = _f32(g)
+        gr, n, H, D = ctx.graph, ctx.graph.n, ctx.H, ctx.D
+        dev = g.device
+        gxl = torch.empty(n, H * D, dtype=torch.float32, device=dev)
+        gatt = torch.empty(H, 2 * D, dtype=torch.float32, device=dev)
+        gT = torch.empty(T.shape[0], H * D, dtype=torch.float32, device=dev)
+        gbias = torch.empty(D, dtype=torch.float32, device=dev)
+        wsb = lib.pgnn_gat_bwd_workspace_bytes(n, gr.e, H, D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.pgnn_gat_bwd(_p(g), g.stride(0), _p(xl), n, H, D, _p(att), _p(T), int(ctx.is_bio), _p(ea), _p(gr.rowptr_t),
+                               _p(gr.nbr_t), _p(gr.eid_t), _p(gr.rowptr_s), _p(gr.nbr_s), _p(gr.eid_s), gr.e, ctx.slope, _p(alpha),
+                               _p(pq), _p(gxl), _p(gatt), _p(gT), _p(gbias), _p(ws), wsb, _st()), "gat_bwd")
+        return gxl, gatt.view(ctx.att_shape), gT, gbias, None, None, None, None, None
+
+
+def gat(xl, att, T, edge_attr, graph, bias, heads=2, slope=0.2, is_bio=False):
+    """GATConv.propagate + update (chem/model.py:148-165): xl = weight_linear(x) [N, heads*D]; att [1, heads, 2D]."""
+    return _Gat.apply(xl, att, T, bias, edge_attr, graph, heads, slope, is_bio)

@@ -14,6 +14,10 @@ checksum is stored so generator drift is detected.  Stored per (domain, gnn_type
     loss                           L = sum(out_train * R), R seeded
     g:<param>                      full gradient for small tensors (< 4096 elements)
     gs0:/gs1:/gp:<param>           column sums / row sums / seeded-probe projection for large ones
+    *64:<param>                    the same summaries from the reference run in float64 (`model.double()`):
+                                   train-mode BatchNorm makes these gradients ill-conditioned in fp32, so
+                                   the parity bound for gradients is stated relative to the reference's OWN
+                                   fp32-vs-fp64 discrepancy (tests/golden_util.py)
     rs:<key>                       BatchNorm running stats after the train-mode forward
 """
 import importlib
@@ -56,14 +60,14 @@ def probe(shape, seed):
     return torch.randn(shape, generator=g)
 
 
-def grad_summaries(name, grad, out):
+def grad_summaries(name, grad, out, tag=""):
     if grad.numel() < 4096:
-        out["g:" + name] = grad.numpy()
+        out["g%s:" % tag + name] = grad.numpy()
     else:
         g2 = grad.reshape(grad.shape[0], -1)
-        out["gs0:" + name] = g2.sum(0).numpy()
-        out["gs1:" + name] = g2.sum(1).numpy()
-        out["gp:" + name] = (grad * probe(grad.shape, 77)).sum().numpy()
+        out["gs0%s:" % tag + name] = g2.sum(0).numpy()
+        out["gs1%s:" % tag + name] = g2.sum(1).numpy()
+        out["gp%s:" % tag + name] = (grad * probe(grad.shape, 77).to(grad.dtype)).sum().numpy()
 
 
 def input_checksum(b):
@@ -95,6 +99,17 @@ def main():
             out["loss"] = loss.detach().numpy()
             for k, p in model.named_parameters():
                 grad_summaries(k, p.grad, out)
+            # the same step in float64 (the conditioning yardstick)
+            m64 = ref.GNN(5, 300, JK="last", drop_ratio=0, gnn_type=t)
+            m64.load_state_dict(P)
+            m64.double().train()
+            ea64 = b["edge_attr"].double() if b["edge_attr"].is_floating_point() else b["edge_attr"]
+            x64 = b["x"].double() if b["x"].is_floating_point() else b["x"]
+            y64 = m64(x64, b["edge_index"], ea64)
+            (y64 * probe(y64.shape, 99).double()).sum().backward()
+            out["out_train64"] = y64.detach().float().numpy()
+            for k, p in m64.named_parameters():
+                grad_summaries(k, p.grad, out, tag="64")
             for k, v in model.state_dict().items():
                 if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
                     out["rs:" + k] = v.numpy()

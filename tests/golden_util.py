@@ -60,11 +60,15 @@ def close_scaled(a, b, tol=1e-4, floor=1.0):
     return e <= tol, e
 
 
-def check_against_golden(G, out_eval, out_train, grads, stats, atol=1e-4, rtol=1e-4, gtol=2e-4):
-    """Compare a full set of results with one golden file. `grads`: name -> tensor; `stats`: name -> tensor."""
+def check_against_golden(G, out_eval, out_train, grads, stats, atol=1e-4, rtol=1e-4, gtol=2e-4, slack=4.0):
+    """Compare a full set of results with one golden file. `grads`: name -> tensor; `stats`: name -> tensor.
+
+    Outputs: |mine - reference_fp32| <= atol + rtol*|ref| (the north_star bound).
+    Gradients: train-mode BatchNorm makes them ill-conditioned in fp32 (the reference's own fp32 and fp64
+    runs differ by up to ~1e-2 of the tensor scale), so the bound is relative to that yardstick:
+        err(mine, ref_fp64) <= max(gtol, slack * err(ref_fp32, ref_fp64)),
+    errors measured against the tensor's largest magnitude (floored at the model's typical gradient scale)."""
     bad = []
-    # floor for the error scale: the model's typical gradient magnitude (a bias feeding a train-mode
-    # BatchNorm has an exactly-zero gradient; its computed value is rounding noise of that scale)
     gmax = sorted(float(np.abs(v).max()) for k, v in G.items() if k.startswith("g:") and v.size)
     floor = max(gmax[len(gmax) // 2], 1.0) if gmax else 1.0
     for name, mine in (("out_eval", out_eval), ("out_train", out_train)):
@@ -73,23 +77,43 @@ def check_against_golden(G, out_eval, out_train, grads, stats, atol=1e-4, rtol=1
         ok, e = close(mine, G[name], atol, rtol)
         if not ok:
             bad.append((name, e))
-    for k, ref in G.items():
+
+    def summarise(kind, t):
+        t = torch.as_tensor(np.asarray(t), dtype=torch.float64)
+        if kind == "g":
+            return t
+        t2 = t.reshape(t.shape[0], -1)
+        if kind == "gs0":
+            return t2.sum(0)
+        if kind == "gs1":
+            return t2.sum(1)
+        return (t * probe(t.shape, 77).double()).sum()
+
+    for k, ref32 in G.items():
         kind, _, name = k.partition(":")
-        if kind == "g" and grads is not None:
-            ok, e = close_scaled(grads[name], ref, gtol, floor)
-        elif kind == "gs0" and grads is not None:
-            g2 = torch.as_tensor(np.asarray(grads[name])).reshape(grads[name].shape[0], -1)
-            ok, e = close_scaled(g2.sum(0), ref, gtol, floor)
-        elif kind == "gs1" and grads is not None:
-            g2 = torch.as_tensor(np.asarray(grads[name])).reshape(grads[name].shape[0], -1)
-            ok, e = close_scaled(g2.sum(1), ref, gtol, floor)
-        elif kind == "gp" and grads is not None:
-            g = torch.as_tensor(np.asarray(grads[name]))
-            ok, e = close_scaled((g * probe(g.shape, 77)).sum(), ref, gtol * 5, floor)
+        if kind in ("g", "gs0", "gs1", "gp") and grads is not None:
+            ref64 = G.get(kind + "64:" + name)
+            mine = summarise(kind, grads[name])
+            if ref64 is None:
+                ok, e = close_scaled(mine, ref32, gtol, floor)
+            else:
+                _, e_ref = close_scaled(ref32, ref64, 0.0, floor)
+                tol = max(gtol, slack * e_ref)
+                ok, e = close_scaled(mine, ref64, tol, floor)
+                if not ok:  # also acceptable: as close to the fp32 reference as that is to fp64
+                    ok, e = close_scaled(mine, ref32, tol, floor)
         elif kind == "rs" and stats is not None:
-            ok, e = close(stats[name], ref, atol, rtol)
+            ok, e = close(stats[name], ref32, atol, rtol)
         else:
             continue
         if not ok:
             bad.append((k, e))
     return bad
+
+
+def grad_close(mine, ref32, ref64, floor=1.0, gtol=2e-4, slack=4.0):
+    """Same yardstick for oracle-based (non-golden) tests: returns (ok, err, tol)."""
+    _, e_ref = close_scaled(ref32, ref64, 0.0, floor)
+    tol = max(gtol, slack * e_ref)
+    ok, e = close_scaled(mine, ref64, tol, floor)
+    return ok, e, tol

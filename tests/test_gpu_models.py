@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import gnn_oracle as O
-from golden_util import TYPES, check_against_golden, golden_batch, golden_params, load, probe
+from golden_util import TYPES, check_against_golden, golden_batch, golden_params, grad_close, load, probe
 
 pytestmark = pytest.mark.gpu
 syn = importlib.import_module("pretrain-gnns_b200.synthetic")
@@ -16,6 +16,26 @@ bio = importlib.import_module("pretrain-gnns_b200.bio.model")
 ops = importlib.import_module("pretrain-gnns_b200.ops")
 DEV = "cuda:0"
 IMPLEMENTED = [t for t in TYPES if t != "gat" or hasattr(ops, "gat")]
+
+
+def _oracle_grads(fn, P):
+    """Run `fn(params) -> scalar loss` on fp32 and fp64 leaf copies of P; returns (grads32, grads64, floor)."""
+    res = []
+    for dt in (torch.float32, torch.float64):
+        L = O.leaf_params(P, dt)
+        fn(L).backward()
+        res.append({k: v.grad for k, v in L.items() if v.requires_grad})
+    mags = sorted(float(v.abs().max()) for v in res[1].values())
+    return res[0], res[1], max(mags[len(mags) // 2], 1e-3)
+
+
+def _check_grads(named_params, g32, g64, floor, prefix=""):
+    bad = []
+    for k, p in named_params:
+        ok, e, tol = grad_close(p.grad.cpu(), g32[prefix + k], g64[prefix + k], floor)
+        if not ok:
+            bad.append((k, e, tol))
+    assert not bad, bad
 
 
 def _dev(b):
@@ -57,19 +77,15 @@ def test_chem_encoder_vs_oracle_b32(t):
         _, out = _run("chem", t, b, P, False)
     err = (out.cpu() - ref).abs()
     assert bool((err <= 1e-4 + 1e-4 * ref.abs()).all()), err.max()
-    L = O.leaf_params(P)
-    ref_t = O.chem_gnn(L, b["x"], b["edge_index"], b["edge_attr"], 5, t, True)
-    R = probe(ref_t.shape, 5)
-    (ref_t * R).sum().backward()
+    R = probe((b["x"].shape[0], 300), 5)
+    ref_t = O.chem_gnn(P, b["x"], b["edge_index"], b["edge_attr"], 5, t, True)
+    g32, g64, floor = _oracle_grads(
+        lambda L: (O.chem_gnn(L, b["x"], b["edge_index"], b["edge_attr"], 5, t, True) * R.to(L["x_embedding1.weight"].dtype)).sum(), P)
     model, out_t = _run("chem", t, b, P, True)
     (out_t * R.to(DEV)).sum().backward()
-    err = (out_t.detach().cpu() - ref_t.detach()).abs()
-    assert bool((err <= 1e-4 + 1e-4 * ref_t.detach().abs()).all()), err.max()
-    gscale = sorted(float(v.grad.abs().max()) for v in L.values() if v.requires_grad)
-    floor = max(gscale[len(gscale) // 2], 1.0)
-    for k, p in model.named_parameters():
-        e = (p.grad.cpu() - L[k].grad).abs().max().item() / max(L[k].grad.abs().max().item(), floor)
-        assert e < 2e-4, (k, e)
+    err = (out_t.detach().cpu() - ref_t).abs()
+    assert bool((err <= 1e-4 + 1e-4 * ref_t.abs()).all()), err.max()
+    _check_grads(model.named_parameters(), g32, g64, floor)
 
 
 def test_chem_graphpred_and_masking_heads():
@@ -112,11 +128,18 @@ def test_contextpred_step_vs_oracle():
     """chem/pretrain_contextpred.py:54-93 with a 5-layer substructure and a 3-layer context encoder."""
     b = syn.substruct_context_batch(16, 4)
     Ps, Pc = O.make_params("chem", "gin", 5, 300, seed=1), O.make_params("chem", "gin", 3, 300, seed=2)
-    Ls, Lc = O.leaf_params(Ps), O.leaf_params(Pc)
-    sub = O.chem_gnn(Ls, b["x_substruct"], b["edge_index_substruct"], b["edge_attr_substruct"], 5, "gin", True)[b["center_substruct_idx"]]
-    ov = O.chem_gnn(Lc, b["x_context"], b["edge_index_context"], b["edge_attr_context"], 3, "gin", True)[b["overlap_context_substruct_idx"]]
-    pos_r, neg_r = O.contextpred_scores(sub, ov, b["batch_overlapped_context"], 16, 1)
-    O.contextpred_loss(pos_r, neg_r).backward()
+    both = {"s." + k: v for k, v in Ps.items()} | {"c." + k: v for k, v in Pc.items()}
+
+    def scores(L):
+        Ls = {k[2:]: v for k, v in L.items() if k.startswith("s.")}
+        Lc = {k[2:]: v for k, v in L.items() if k.startswith("c.")}
+        sub = O.chem_gnn(Ls, b["x_substruct"], b["edge_index_substruct"], b["edge_attr_substruct"], 5, "gin", True)[b["center_substruct_idx"]]
+        ov = O.chem_gnn(Lc, b["x_context"], b["edge_index_context"], b["edge_attr_context"], 3, "gin", True)[b["overlap_context_substruct_idx"]]
+        return O.contextpred_scores(sub, ov, b["batch_overlapped_context"], 16, 1)
+
+    with torch.no_grad():
+        pos_r, neg_r = scores(both)
+    g32, g64, floor = _oracle_grads(lambda L: O.contextpred_loss(*scores(L)), both)
     ms, mc = chem.GNN(5, 300), chem.GNN(3, 300)
     ms.load_state_dict(Ps); mc.load_state_dict(Pc)
     ms.to(DEV).train(); mc.to(DEV).train()
@@ -128,11 +151,8 @@ def test_contextpred_step_vs_oracle():
     O.contextpred_loss(pos, neg).backward()
     assert torch.allclose(pos.detach().cpu(), pos_r.detach(), atol=2e-4, rtol=1e-4)
     assert torch.allclose(neg.detach().cpu(), neg_r.detach(), atol=2e-4, rtol=1e-4)
-    for model, L in ((ms, Ls), (mc, Lc)):
-        for k, p in model.named_parameters():
-            ref = L[k].grad
-            e = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-2)
-            assert e < 5e-4, (k, e)
+    _check_grads(ms.named_parameters(), g32, g64, floor, "s.")
+    _check_grads(mc.named_parameters(), g32, g64, floor, "c.")
 
 
 def test_bio_graphpred_vs_oracle():
@@ -142,10 +162,15 @@ def test_bio_graphpred_vs_oracle():
     full = {"gnn." + k: v for k, v in P.items()}
     full["graph_pred_linear.weight"] = torch.randn(40, 600, generator=g) * 0.03
     full["graph_pred_linear.bias"] = torch.randn(40, generator=g) * 0.03
-    L = O.leaf_params(full)
-    ref = O.bio_graphpred(L, b["x"], b["edge_index"], b["edge_attr"], b["batch"], b["center_node_idx"], 3, 5, "gin", True)
     y = b["go_target_pretrain"].view(3, 40).double()
-    torch.nn.functional.binary_cross_entropy_with_logits(ref.double(), y).backward()
+
+    def logits(L):
+        return O.bio_graphpred(L, b["x"].to(L["graph_pred_linear.bias"].dtype), b["edge_index"],
+                               b["edge_attr"].to(L["graph_pred_linear.bias"].dtype), b["batch"], b["center_node_idx"], 3, 5, "gin", True)
+
+    with torch.no_grad():
+        ref = logits(full)
+    g32, g64, floor = _oracle_grads(lambda L: torch.nn.functional.binary_cross_entropy_with_logits(logits(L).double(), y), full)
     model = bio.GNN_graphpred(5, 300, 40)
     model.load_state_dict(full)
     model.to(DEV).train()
@@ -153,10 +178,7 @@ def test_bio_graphpred_vs_oracle():
     out = model(d)
     torch.nn.functional.binary_cross_entropy_with_logits(out.double(), y.to(DEV)).backward()
     assert torch.allclose(out.detach().cpu(), ref.detach(), atol=1e-4, rtol=1e-4)
-    for k, p in model.named_parameters():
-        r = L[k].grad
-        e = (p.grad.cpu() - r).abs().max().item() / max(r.abs().max().item(), 1e-3)
-        assert e < 5e-4, (k, e)
+    _check_grads(model.named_parameters(), g32, g64, floor)
 
 
 def test_full_size_properties_b256():
