@@ -33,14 +33,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // byte sizes of one operand buffer (hi or lo) for a tile of R rows (MN extent) x BK
 __host__ __device__ constexpr int kmajor_lbo(int R) { return R * 16 + 32; }          // stride between 16-byte k-chunks
 __host__ __device__ constexpr int kmajor_bytes(int R) { return kmajor_lbo(R) * (BK / 4); }
-__host__ __device__ constexpr int mnmajor_lbo(int R) { return (R / 4) * 128; }        // stride between 8-deep k-blocks
-__host__ __device__ constexpr int mnmajor_bytes(int R) { return mnmajor_lbo(R) * (BK / 8); }
+// MN-major tf32 operands must use the 128B-swizzle-with-32B-base layout (UMMA layout type 1): atoms of
+// [4 k][32 consecutive row indices] = 4 rows of 128 B, the 32-byte chunk index XOR-ed with (k mod 4).
+// A tile keeps the BK/4 atoms of one 32-row block contiguous: k-group stride (SBO) 512 B, block stride (LBO) 4 KiB.
+constexpr int MN_SBO = 512;
+constexpr int MN_LBO = (BK / 4) * MN_SBO;
+__host__ __device__ constexpr int mnmajor_bytes(int R) { return (R / 32) * MN_LBO; }
 
-// UMMA shared-memory matrix descriptor, no swizzle (layout_type 0), version 1 (sm_100).
-// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+// UMMA shared-memory matrix descriptor, version 1 (sm_100).
+// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout type
+// (0 = no swizzle, 1 = 128B swizzle with 32B base)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
-         ((uint64_t)1 << 46);
+         ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
 }
 
 // instruction descriptor for kind::tf32, fp32 accumulate
@@ -65,11 +70,17 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// Bounded spin: a lost arrival traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Time-bounded wait: a lost arrival traps after ~2 s (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  const uint64_t t0 = globaltimer_ns();
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 28); ++it) {
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -80,6 +91,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
+    if ((it & 1023u) == 1023u && globaltimer_ns() - t0 > 2000000000ull) break;
   }
   asm volatile("trap;");
 }
@@ -108,6 +120,8 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
   hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
   lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
 }
+
+__device__ int g_tc_mn_variant = 0;  // development switch for the MN-major descriptor convention
 
 struct TcEpilogue {
   const float* bias;      // [N] or null
@@ -157,8 +171,8 @@ struct Operand {
           const int r = f / (BK / 4), kc = f % (BK / 4);
           off = kc * kmajor_lbo(R) + (r >> 3) * 128 + (r & 7) * 16;
         } else {
-          const int k = f / (R / 4), rc = f % (R / 4);
-          off = (k >> 3) * mnmajor_lbo(R) + rc * 128 + (k & 7) * 16;
+          const int k = f / (R / 4), rc = f % (R / 4);  // rc: group of 4 consecutive row indices
+          off = (rc >> 3) * MN_LBO + (k >> 2) * MN_SBO + (k & 3) * 128 + ((((rc >> 1) & 3) ^ (k & 3)) << 5) + (rc & 1) * 16;
         }
         float4 hi, lo;
         split4(v[i], hi, lo);
@@ -170,7 +184,8 @@ struct Operand {
   // descriptor of k-step j (8 reduction elements) inside a staged buffer
   __device__ __forceinline__ static uint64_t desc(uint32_t base, int j) {
     if (KC) return umma_desc(base + 2 * j * kmajor_lbo(R), kmajor_lbo(R), 128);
-    return umma_desc(base + j * mnmajor_lbo(R), mnmajor_lbo(R), 128);
+    if (g_tc_mn_variant == 1) return umma_desc(base + j * 2 * MN_SBO, MN_SBO, MN_LBO, 1);
+    return umma_desc(base + j * 2 * MN_SBO, MN_LBO, MN_SBO, 1);  // k-step = 8 k = two 4-deep atoms
   }
 };
 
@@ -360,6 +375,22 @@ int dispatch(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, f
 
 }  // namespace
 
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_set_tc_variant(int v) {
+  return cudaMemcpyToSymbol(g_tc_mn_variant, &v, sizeof(int)) == cudaSuccess ? 0 : -2;
+}
+
+// development entry: C[M,N] = sum_r A(m,r) B(n,r) with explicit operand majors (1 = reduction-contiguous)
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_tc_gemm(int a_kc, int b_kc, int bn, const float* A, int64_t lda,
+                                                                        const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+                                                                        int N, int K, void* stream) {
+  TcEpilogue ep{nullptr, 0, nullptr, 0, 0};
+  cudaStream_t st = as_stream(stream);
+  if (a_kc && b_kc) return dispatch<true, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
+  if (a_kc && !b_kc) return dispatch<true, false>(bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
+  if (!a_kc && b_kc) return dispatch<false, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
+  return dispatch<false, false>(bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
+}
+
 // y[M,N] = act(x[M,K] . w[N,K]^T + bias)
 int pgnn_tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, int64_t M, int64_t N, int64_t K, int relu,
                        float* y, int64_t ldy, cudaStream_t st) {
@@ -385,6 +416,8 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
   const int bn = pick_bn((int)N, (int)K, 1);
   const int tiles = (int)(ceil_div(N, BM) * ceil_div(K, bn));
   int splits = (int)ceil_div(kNumSMs, tiles);
+  // the tensor core accumulates with truncation: keep each TMEM chain <= 1024 rows, fold the rest in fp32 atomics
+  if (splits < (int)ceil_div(M, 1024)) splits = (int)ceil_div(M, 1024);
   const int max_splits = (int)ceil_div(M, 2 * BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
