@@ -180,7 +180,7 @@ def run_b200(args, rank, world, local_rank):
     model = chem.GNN(NUM_LAYER, EMB, JK="last", drop_ratio=0, gnn_type="gin").to(dev).train()
     head = torch.nn.Linear(EMB, 119).to(dev)
     params = list(model.parameters()) + list(head.parameters())
-    reducer = pdist.GradAllReducer(params) if world > 1 else None
+    reducer = pdist.GradAllReducer(params, flat_sources=[pdist.encoder_flat_source(model)]) if world > 1 else None
 
     host = make_batches(syn, rank, NUM_DISTINCT_BATCHES)
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]

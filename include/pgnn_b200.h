@@ -223,6 +223,33 @@ PGNN_API int pgnn_shifted_rowdot_bwd(const float* g, const float* a, int64_t lda
                                      int64_t B, int64_t C, int64_t shift, int accumulate,
                                      float* ga, int64_t ldga, float* gb, int64_t ldgb, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Whole-encoder entry points: chem GNN with gnn_type="gin", JK="last", drop_ratio=0 (chem/model.py:255-290).
+ * What GNN.forward / loss.backward() bind to: two boundary crossings per training step.
+ *
+ * params: HOST array of num_params = 2 + 8*L DEVICE pointers in state_dict order
+ *   [x_embedding1.weight, x_embedding2.weight,
+ *    then per layer l: gnns.l.mlp.0.weight, .mlp.0.bias, .mlp.2.weight, .mlp.2.bias,
+ *                      gnns.l.edge_embedding1.weight, .edge_embedding2.weight, batch_norms.l.weight, .bias]
+ * bn_running_mean / bn_running_var / bn_num_batches_tracked: HOST arrays of L device pointers (updated in
+ *   training mode exactly as torch.nn.BatchNorm1d does; bn_num_batches_tracked may be NULL).
+ * workspace: device scratch of pgnn_chem_gin_workspace_bytes; forward leaves the bucketed graph and the saved
+ *   activations in it, backward consumes them, so the SAME workspace must be passed to both.
+ * grads: ONE flat fp32 buffer; tensor i of the params order lives at [offsets[i], offsets[i+1]) with offsets from
+ *   pgnn_chem_gin_grad_offsets (host array of num_params + 1 entries).  OVERWRITTEN.
+ * ------------------------------------------------------------------------------------------- */
+PGNN_API int64_t pgnn_chem_gin_num_params(int64_t L);
+PGNN_API int pgnn_chem_gin_grad_offsets(int64_t L, int64_t D, int64_t* offsets);
+PGNN_API int64_t pgnn_chem_gin_workspace_bytes(int64_t N, int64_t E, int64_t L, int64_t D);
+PGNN_API int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mean, void* const* bn_running_var,
+                                   void* const* bn_num_batches_tracked, const int64_t* x, const int64_t* edge_index,
+                                   const int64_t* edge_attr, int64_t N, int64_t E, int64_t L, int64_t D, int training,
+                                   float momentum, float eps, int precision, float* node_rep, int64_t ld_out,
+                                   void* workspace, int64_t workspace_bytes, void* stream);
+PGNN_API int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, int64_t ldg, const int64_t* x,
+                                    int64_t N, int64_t E, int64_t L, int64_t D, int precision, float* grads,
+                                    void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

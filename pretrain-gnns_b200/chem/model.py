@@ -146,6 +146,19 @@ class GNN(nn.Module):
             raise ValueError("unknown gnn_type %r" % (gnn_type,))
         self.gnns = nn.ModuleList([_CONVS[gnn_type](emb_dim) for _ in range(num_layer)])
         self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
+        self._gnn_type = gnn_type
+        self._plan = None          # lazily built bookkeeping of the fused GIN path (ops.ChemGinPlan)
+        self.fused = True          # set False to force the layer-by-layer composition (used by the tests)
+
+    def _fused_plan(self):
+        """The whole-encoder kernels cover gnn_type='gin', JK='last', sum aggregation, no live dropout."""
+        if not (self.fused and self._gnn_type == "gin" and self.JK == "last" and (self.drop_ratio == 0 or not self.training)):
+            return None
+        if any(conv.aggr != "add" for conv in self.gnns) or any(bn.training != self.training for bn in self.batch_norms):
+            return None
+        if self._plan is None:
+            self._plan = ops.ChemGinPlan(self)
+        return self._plan
 
     def forward(self, *argv):
         if len(argv) == 3:
@@ -154,6 +167,9 @@ class GNN(nn.Module):
             x, edge_index, edge_attr = argv[0].x, argv[0].edge_index, argv[0].edge_attr
         else:
             raise ValueError("unmatched number of arguments.")
+        plan = self._fused_plan()
+        if plan is not None:
+            return ops.chem_gin_encoder(plan, x, edge_index, edge_attr, self.training)
         graph = ops.graph_for(edge_index, x.size(0))
         h = ops.chem_embed(x, self.x_embedding1.weight, self.x_embedding2.weight)
         hs = [h]

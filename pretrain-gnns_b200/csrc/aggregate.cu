@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256)
 k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restrict__ in_scale,
                 const float* __restrict__ in_shift, int in_relu, int64_t n, int C4, const int* __restrict__ rowptr,
                 const int* __restrict__ nbr, int mode, const float* __restrict__ dinv, const float* __restrict__ S, int Q,
-                const float* __restrict__ T, int64_t edge_off, float* __restrict__ out, int64_t ldo) {
+                const float* __restrict__ T, const float* __restrict__ T2, int q_split, int64_t edge_off, float* __restrict__ out,
+                int64_t ldo) {
   const int64_t total = n * C4;
   const int C = C4 * 4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -90,7 +91,7 @@ k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restric
       const float* s = S + (int64_t)i * Q;
       for (int q = 0; q < Q; ++q) {
         const float w = s[q];
-        const float4 t = ld4(T + (int64_t)q * C + c);
+        const float4 t = ld4(q < q_split ? T + (int64_t)q * C + c : T2 + (int64_t)(q - q_split) * C + c);
         e.x = fmaf(w, t.x, e.x);
         e.y = fmaf(w, t.y, e.y);
         e.z = fmaf(w, t.z, e.z);
@@ -149,7 +150,7 @@ constexpr int kTblRows = 128;
 constexpr int kMaxQ = 16;
 __global__ void __launch_bounds__(128)
 k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g, int64_t ldg, int64_t g_off, int64_t n,
-                 int C, float* __restrict__ gT, int64_t ldt) {
+                 int C, float* __restrict__ gT, int64_t ldt, float* __restrict__ gT2, int q_split) {
   __shared__ float s_S[kTblRows * kMaxQ];
   const int64_t r0 = (int64_t)blockIdx.x * kTblRows;
   const int rows = (int)((n - r0) < kTblRows ? (n - r0) : kTblRows);
@@ -168,7 +169,7 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
   }
 #pragma unroll
   for (int q = 0; q < kMaxQ; ++q)
-    if (q < Q) atomicAdd(&gT[(int64_t)q * ldt + c], acc[q]);
+    if (q < Q) atomicAdd(q < q_split ? &gT[(int64_t)q * ldt + c] : &gT2[(int64_t)(q - q_split) * ldt + c], acc[q]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -235,12 +236,33 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
-// shared with gat.cu: gT[q*ldt + c] += sum_i S[i][q] g[i][g_off + c]  (caller zeroes gT)
-int pgnn_internal_edge_table_bwd(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
-                                 int64_t ldt, cudaStream_t st) {
+// shared with gat.cu / encoder.cu: gT[q*ldt + c] += sum_i S[i][q] g[i][g_off + c]  (caller zeroes gT).
+// Rows q >= q_split go to gT2 (the two bond tables of chem/model.py:30-31 are separate parameters).
+int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
+                                  int64_t ldt, float* gT2, int q_split, cudaStream_t st) {
   if (n == 0) return PGNN_OK;
   dim3 grid((unsigned)ceil_div(n, kTblRows), (unsigned)ceil_div(C, 128));
-  k_edge_table_bwd<<<grid, 128, 0, st>>>(S, Q, g, ldg, g_off, n, C, gT, ldt);
+  k_edge_table_bwd<<<grid, 128, 0, st>>>(S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+int pgnn_internal_edge_table_bwd(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
+                                 int64_t ldt, cudaStream_t st) {
+  return pgnn_internal_edge_table_bwd2(S, Q, g, ldg, g_off, n, C, gT, ldt, nullptr, Q, st);
+}
+
+// aggregate forward with the table given as two row blocks (T rows [0,q_split), T2 rows [q_split,Q))
+int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
+                                int64_t num_nodes, int64_t C, const int32_t* rowptr_t, const int32_t* nbr_t, int mode, const float* dinv,
+                                const float* S, int64_t Q, const float* T, const float* T2, int q_split, int64_t edge_off, float* out,
+                                int64_t ldo, cudaStream_t st) {
+  if (num_nodes == 0) return PGNN_OK;
+  if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out) || (T && !aligned16(T)) || (T2 && !aligned16(T2)) ||
+      (in_scale && (!aligned16(in_scale) || !aligned16(in_shift))))
+    return PGNN_EUNSUPPORTED;
+  const int C4 = (int)(C / 4);
+  k_aggregate_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, st>>>(x, ldx, in_scale, in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t,
+                                                                  mode, dinv, S, (int)Q, T, T2, q_split, edge_off, out, ldo);
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -257,14 +279,8 @@ int pgnn_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const
   PGNN_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr));
   PGNN_CHECK_ARG(!S || (T && Q > 0 && Q <= kMaxQ));
   PGNN_CHECK_ARG(edge_off == 0 || (S && edge_off % 4 == 0));
-  if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out) || (T && !aligned16(T)) ||
-      (in_scale && (!aligned16(in_scale) || !aligned16(in_shift))))
-    return PGNN_EUNSUPPORTED;
-  const int C4 = (int)(C / 4);
-  k_aggregate_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(
-      x, ldx, in_scale, in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t, mode, dinv, S, (int)Q, T, edge_off, out, ldo);
-  PGNN_LAUNCH_CHECK();
-  return PGNN_OK;
+  return pgnn_internal_aggregate_fwd(x, ldx, in_scale, in_shift, in_relu, num_nodes, C, rowptr_t, nbr_t, mode, dinv, S, Q, T, nullptr,
+                                     (int)Q, edge_off, out, ldo, as_stream(stream));
 }
 
 int pgnn_aggregate_bwd(const float* g, int64_t ldg, int64_t num_nodes, int64_t C, const int32_t* rowptr_s,

@@ -31,7 +31,7 @@ constexpr int NSTAGE = 2;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // byte sizes of one operand buffer (hi or lo) for a tile of R rows (MN extent) x BK
-__host__ __device__ constexpr int kmajor_lbo(int R) { return R * 16 + 32; }          // stride between 16-byte k-chunks
+__host__ __device__ constexpr int kmajor_lbo(int R) { return R * 16 + 16; }          // stride between 16-byte k-chunks (+16: the 8 chunks of a row hit 8 distinct bank groups)
 __host__ __device__ constexpr int kmajor_bytes(int R) { return kmajor_lbo(R) * (BK / 4); }
 // MN-major tf32 operands must use the 128B-swizzle-with-32B-base layout (UMMA layout type 1): atoms of
 // [4 k][32 consecutive row indices] = 4 rows of 128 B, the 32-byte chunk index XOR-ed with (k mod 4).
@@ -139,7 +139,8 @@ template <bool KC, int R>
 struct Operand {
   static constexpr int VEC = R * BK / 4;
   static constexpr int NV = (VEC + NTHREADS - 1) / NTHREADS;
-  static constexpr int BYTES = KC ? kmajor_bytes(R) : mnmajor_bytes(R);
+  // rounded to 1 KiB so that every buffer (the swizzled MN-major ones need 512 B atoms) starts aligned
+  static constexpr int BYTES = ((KC ? kmajor_bytes(R) : mnmajor_bytes(R)) + 1023) / 1024 * 1024;
   float4 v[NV];
 
   __device__ __forceinline__ void fetch(const float* __restrict__ src, int64_t ld, int r0, int rows, int k0, int kend) {
@@ -238,20 +239,26 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   const uint32_t tmem_acc = tmem_base_s;
   constexpr uint32_t idesc = umma_idesc(BM, BN, !A_KC, !B_KC);
 
-  OpA ra;
-  OpB rb;
+  // Register double-buffering: the global loads of block kb+2 are issued before block kb+1 is split, so a
+  // load has two block-times (2 x 12 MMAs) to arrive and HBM/L2 latency stays off the critical path.
+  OpA ra[2];
+  OpB rb[2];
   if (nkb > 0) {
-    ra.fetch(A, lda, m0, M, kbeg, kend);
-    rb.fetch(B, ldb, n0, N, kbeg, kend);
+    ra[0].fetch(A, lda, m0, M, kbeg, kend);
+    rb[0].fetch(B, ldb, n0, N, kbeg, kend);
   }
-  for (int kb = 0; kb < nkb; ++kb) {
+  if (nkb > 1) {
+    ra[1].fetch(A, lda, m0, M, kbeg + BK, kend);
+    rb[1].fetch(B, ldb, n0, N, kbeg + BK, kend);
+  }
+  auto block = [&](int kb, OpA& qa, OpB& qb) {
     const int s = kb & 1;
     if (kb >= NSTAGE) mbar_wait(smem_u32(&mma_done[s]), ((kb / NSTAGE) - 1) & 1);  // MMAs of block kb-2 released stage s
-    ra.stash(a_hi(s), a_lo(s));
-    rb.stash(b_hi(s), b_lo(s));
-    if (kb + 1 < nkb) {  // next block's global loads fly while this block's MMAs run
-      ra.fetch(A, lda, m0, M, kbeg + (kb + 1) * BK, kend);
-      rb.fetch(B, ldb, n0, N, kbeg + (kb + 1) * BK, kend);
+    qa.stash(a_hi(s), a_lo(s));
+    qb.stash(b_hi(s), b_lo(s));
+    if (kb + 2 < nkb) {
+      qa.fetch(A, lda, m0, M, kbeg + (kb + 2) * BK, kend);
+      qb.fetch(B, ldb, n0, N, kbeg + (kb + 2) * BK, kend);
     }
     fence_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
@@ -270,6 +277,10 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
       }
       __syncwarp();
     }
+  };
+  for (int kb = 0; kb < nkb; kb += 2) {  // unrolled by two so the register sets are addressed statically
+    block(kb, ra[0], rb[0]);
+    if (kb + 1 < nkb) block(kb + 1, ra[1], rb[1]);
   }
   if (nkb > 0) {
     const int last = nkb - 1;

@@ -1,0 +1,205 @@
+// Whole-encoder entry points for the chem GIN stack (chem/model.py:255-290 with gnn_type="gin", JK="last",
+// drop_ratio=0): ONE call enqueues graph preparation, the atom embedding and all L x (aggregate -> MLP ->
+// BatchNorm[-> ReLU]) layers; a second call enqueues the whole backward.  This is what GNN.forward binds
+// to, so a training step crosses the Python/C boundary twice instead of ~60 times, and the inter-layer
+// BatchNorm + ReLU never makes a pass of its own: layer l only accumulates the batch statistics and layer
+// l+1's gather applies scale/shift/ReLU while it loads the rows (pgnn_aggregate_fwd's in_scale/in_shift).
+//
+// Parameters arrive as a host array of device pointers in a fixed order (PGNN_CHEM_GIN_* below), gradients
+// leave in ONE flat fp32 buffer with the library-defined layout of pgnn_chem_gin_grad_offsets, which is
+// also the buffer the data-parallel all-reduce runs on.
+#include "common.cuh"
+
+int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
+                                  int64_t ldt, float* gT2, int q_split, cudaStream_t st);
+int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
+                                int64_t num_nodes, int64_t C, const int32_t* rowptr_t, const int32_t* nbr_t, int mode, const float* dinv,
+                                const float* S, int64_t Q, const float* T, const float* T2, int q_split, int64_t edge_off, float* out,
+                                int64_t ldo, cudaStream_t st);
+
+namespace {
+
+// order of the parameter pointer table and of the flat gradient layout
+enum { P_XEMB1 = 0, P_XEMB2 = 1, P_LAYER0 = 2 };
+enum { L_W1 = 0, L_B1, L_W2, L_B2, L_ET1, L_ET2, L_GAMMA, L_BETA, L_COUNT };
+
+struct Carve {
+  char* base;
+  int64_t off = 0;
+  explicit Carve(void* b) : base(reinterpret_cast<char*>(b)) {}
+  template <typename T>
+  T* take(int64_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(count * (int64_t)sizeof(T), 256);
+    return p;
+  }
+};
+
+struct Ws {
+  int32_t *rowptr_t, *rowptr_s, *nbr_t, *eid_t, *nbr_s, *eid_s;
+  float *S, *h0, *scale, *shift, *mean, *invstd;  // scale/shift/mean/invstd: [L, D]
+  float *aggr, *z1, *z2;                           // [L, N, D], [L, N, 2D], [L, N, D]
+  float *gh, *gz2, *gz1, *gaggr;                   // backward temporaries
+  void* scratch;                                   // bucket / BatchNorm scratch
+  int64_t scratch_bytes, total;
+};
+
+Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
+  Carve c(base);
+  Ws w;
+  const int64_t e1 = E > 0 ? E : 1;
+  w.rowptr_t = c.take<int32_t>(N + 1);
+  w.rowptr_s = c.take<int32_t>(N + 1);
+  w.nbr_t = c.take<int32_t>(e1);
+  w.eid_t = c.take<int32_t>(e1);
+  w.nbr_s = c.take<int32_t>(e1);
+  w.eid_s = c.take<int32_t>(e1);
+  w.S = c.take<float>(N * 9);
+  w.h0 = c.take<float>(N * D);
+  w.scale = c.take<float>(L * D);
+  w.shift = c.take<float>(L * D);
+  w.mean = c.take<float>(L * D);
+  w.invstd = c.take<float>(L * D);
+  w.aggr = c.take<float>(L * N * D);
+  w.z1 = c.take<float>(L * N * 2 * D);
+  w.z2 = c.take<float>(L * N * D);
+  w.gh = c.take<float>(N * D);
+  w.gz2 = c.take<float>(N * D);
+  w.gz1 = c.take<float>(N * 2 * D);
+  w.gaggr = c.take<float>(N * D);
+  int64_t sb = pgnn_graph_prep_workspace_bytes(N, E);
+  const int64_t bb = pgnn_bn_workspace_bytes(N > 0 ? N : 1, D);
+  if (bb > sb) sb = bb;
+  w.scratch_bytes = sb;
+  w.scratch = c.take<char>(sb);
+  w.total = c.off;
+  return w;
+}
+
+#define TRY(call)                 \
+  do {                            \
+    int rc__ = (call);            \
+    if (rc__ != PGNN_OK) return rc__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int64_t pgnn_chem_gin_num_params(int64_t L) { return L < 1 ? PGNN_EINVAL : 2 + L_COUNT * L; }
+
+int pgnn_chem_gin_grad_offsets(int64_t L, int64_t D, int64_t* offsets /*host [num_params + 1]*/) {
+  PGNN_CHECK_ARG(L >= 1 && D > 0 && offsets);
+  int64_t o = 0, i = 0;
+  offsets[i++] = o; o += 120 * D;  // x_embedding1.weight
+  offsets[i++] = o; o += 3 * D;    // x_embedding2.weight
+  for (int64_t l = 0; l < L; ++l) {
+    offsets[i++] = o; o += 2 * D * D;  // mlp.0.weight [2D, D]
+    offsets[i++] = o; o += 2 * D;      // mlp.0.bias
+    offsets[i++] = o; o += 2 * D * D;  // mlp.2.weight [D, 2D]
+    offsets[i++] = o; o += D;          // mlp.2.bias
+    offsets[i++] = o; o += 6 * D;      // edge_embedding1.weight
+    offsets[i++] = o; o += 3 * D;      // edge_embedding2.weight
+    offsets[i++] = o; o += D;          // batch_norms.l.weight
+    offsets[i++] = o; o += D;          // batch_norms.l.bias
+  }
+  offsets[i] = o;
+  return PGNN_OK;
+}
+
+int64_t pgnn_chem_gin_workspace_bytes(int64_t N, int64_t E, int64_t L, int64_t D) {
+  if (N < 0 || E < 0 || L < 1 || D <= 0) return PGNN_EINVAL;
+  return carve(nullptr, N, E, L, D).total;
+}
+
+int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mean, void* const* bn_running_var,
+                          void* const* bn_num_batches_tracked, const int64_t* x, const int64_t* edge_index,
+                          const int64_t* edge_attr, int64_t N, int64_t E, int64_t L, int64_t D, int training, float momentum, float eps,
+                          int precision, float* node_rep, int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  PGNN_CHECK_ARG(N >= 0 && E >= 0 && L >= 1 && D > 0 && D % 4 == 0 && params && bn_running_mean && bn_running_var && workspace);
+  PGNN_CHECK_ARG(N == 0 || (x && node_rep));
+  if (workspace_bytes < pgnn_chem_gin_workspace_bytes(N, E, L, D)) return PGNN_EWORKSPACE;
+  if (N == 0) return PGNN_OK;
+  if (training && N < 1) return PGNN_EINVAL;
+  Ws w = carve(workspace, N, E, L, D);
+  TRY(pgnn_graph_prep(edge_index, E, N, w.rowptr_t, w.nbr_t, w.eid_t, w.rowptr_s, w.nbr_s, w.eid_s, w.scratch, w.scratch_bytes, stream));
+  TRY(pgnn_chem_edge_summary(edge_attr, w.rowptr_t, w.nbr_t, w.eid_t, N, PGNN_AGG_SUM, nullptr, w.S, stream));
+  TRY(pgnn_chem_embed_fwd(x, (const float*)params[P_XEMB1], (const float*)params[P_XEMB2], N, D, w.h0, D, stream));
+  const float* h = w.h0;            // input rows of the current layer (pre-affine)
+  const float *in_scale = nullptr, *in_shift = nullptr;
+  for (int64_t l = 0; l < L; ++l) {
+    const void* const* p = params + P_LAYER0 + l * L_COUNT;
+    float* aggr = w.aggr + l * N * D;
+    float* z1 = w.z1 + l * N * 2 * D;
+    float* z2 = w.z2 + l * N * D;
+    const bool last = (l == L - 1);
+    TRY(pgnn_internal_aggregate_fwd(h, D, in_scale, in_shift, in_scale != nullptr, N, D, w.rowptr_t, w.nbr_t, PGNN_AGG_SUM, nullptr, w.S, 9,
+                                    (const float*)p[L_ET1], (const float*)p[L_ET2], 6, 0, aggr, D, as_stream(stream)));
+    TRY(pgnn_linear_fwd(aggr, D, (const float*)p[L_W1], (const float*)p[L_B1], N, 2 * D, D, 1, z1, 2 * D, precision, stream));
+    TRY(pgnn_linear_fwd(z1, 2 * D, (const float*)p[L_W2], (const float*)p[L_B2], N, D, 2 * D, 0, z2, D, precision, stream));
+    if (training) {
+      // statistics only for inner layers (applied on load by the next gather); the last layer materialises node_rep
+      TRY(pgnn_bn_fwd_train(z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], (float*)bn_running_mean[l],
+                            (float*)bn_running_var[l], bn_num_batches_tracked ? (int64_t*)bn_num_batches_tracked[l] : nullptr, momentum,
+                            eps, 0, last ? node_rep : nullptr, ld_out, w.mean + l * D, w.invstd + l * D, w.scale + l * D,
+                            w.shift + l * D, w.scratch, w.scratch_bytes, stream));
+      h = z2;
+      in_scale = w.scale + l * D;
+      in_shift = w.shift + l * D;
+    } else {
+      // eval: plain BN(+ReLU) pass with the running statistics, ping-ponging between two spare buffers
+      float* y = last ? node_rep : ((l & 1) ? w.gz2 : w.gaggr);
+      TRY(pgnn_bn_fwd_eval(z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], (const float*)bn_running_mean[l],
+                           (const float*)bn_running_var[l], eps, !last, y, last ? ld_out : D, stream));
+      h = y;
+      in_scale = in_shift = nullptr;
+    }
+  }
+  return PGNN_OK;
+}
+
+int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, int64_t ldg, const int64_t* x, int64_t N, int64_t E,
+                           int64_t L, int64_t D, int precision, float* grads, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
+  PGNN_CHECK_ARG(N >= 0 && E >= 0 && L >= 1 && D > 0 && D % 4 == 0 && params && grads && workspace);
+  if (workspace_bytes < pgnn_chem_gin_workspace_bytes(N, E, L, D)) return PGNN_EWORKSPACE;
+  int64_t off[2 + L_COUNT * 64 + 1];
+  PGNN_CHECK_ARG(L <= 64);
+  pgnn_chem_gin_grad_offsets(L, D, off);
+  cudaStream_t st = as_stream(stream);
+  if (N == 0) {
+    PGNN_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * off[2 + L_COUNT * L], st));
+    return PGNN_OK;
+  }
+  PGNN_CHECK_ARG(g_node_rep && x);
+  Ws w = carve(workspace, N, E, L, D);
+  const float* gy = g_node_rep;
+  int64_t ldgy = ldg;
+  for (int64_t l = L - 1; l >= 0; --l) {
+    const void* const* p = params + P_LAYER0 + l * L_COUNT;
+    const int64_t* o = off + P_LAYER0 + l * L_COUNT;
+    const float* aggr = w.aggr + l * N * D;
+    const float* z1 = w.z1 + l * N * 2 * D;
+    const float* z2 = w.z2 + l * N * D;
+    const bool last = (l == L - 1);
+    // BatchNorm (+ReLU mask recomputed from z2) backward
+    TRY(pgnn_bn_bwd(gy, ldgy, z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], w.mean + l * D, w.invstd + l * D, !last,
+                    w.gz2, D, grads + o[L_GAMMA], grads + o[L_BETA], w.scratch, w.scratch_bytes, stream));
+    // MLP backward
+    TRY(pgnn_linear_bwd_w(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], grads + o[L_B2], precision, stream));
+    TRY(pgnn_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, precision, stream));
+    TRY(pgnn_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], grads + o[L_B1], precision, stream));
+    TRY(pgnn_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, precision, stream));
+    // bond tables: gT = S^T gaggr, rows 0..5 -> edge_embedding1, 6..8 -> edge_embedding2
+    PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));  // the two tables are adjacent in the layout
+    TRY(pgnn_internal_edge_table_bwd2(w.S, 9, w.gaggr, D, 0, N, (int)D, grads + o[L_ET1], D, grads + o[L_ET2], 6, st));
+    // transpose-graph gather: gradient w.r.t. this layer's input rows
+    TRY(pgnn_aggregate_bwd(w.gaggr, D, N, D, w.rowptr_s, w.nbr_s, PGNN_AGG_SUM, nullptr, w.rowptr_t, w.gh, D, stream));
+    gy = w.gh;
+    ldgy = D;
+  }
+  TRY(pgnn_chem_embed_bwd(x, w.gh, D, N, D, grads + off[P_XEMB1], 120, grads + off[P_XEMB2], 3, stream));
+  return PGNN_OK;
+}
+
+}  // extern "C"

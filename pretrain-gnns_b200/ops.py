@@ -553,3 +553,89 @@ class _Gat(Function):
 def gat(xl, att, T, edge_attr, graph, bias, heads=2, slope=0.2, is_bio=False):
     """GATConv.propagate + update (chem/model.py:148-165): xl = weight_linear(x) [N, heads*D]; att [1, heads, 2D]."""
     return _Gat.apply(xl, att, T, bias, edge_attr, graph, heads, slope, is_bio)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-encoder fast path: chem GIN (pgnn_chem_gin_forward / pgnn_chem_gin_backward)
+# ------------------------------------------------------------------------------------------------
+import ctypes as _ct
+
+
+class ChemGinPlan:
+    """Per-module bookkeeping for the fused chem GIN encoder: parameter order, gradient layout, pointer tables."""
+
+    def __init__(self, gnn):
+        self.L = len(gnn.gnns)
+        self.D = gnn.x_embedding1.weight.shape[1]
+        ps = [gnn.x_embedding1.weight, gnn.x_embedding2.weight]
+        for conv, bn in zip(gnn.gnns, gnn.batch_norms):
+            ps += [conv.mlp[0].weight, conv.mlp[0].bias, conv.mlp[2].weight, conv.mlp[2].bias,
+                   conv.edge_embedding1.weight, conv.edge_embedding2.weight, bn.weight, bn.bias]
+        self.params = ps
+        n = len(ps)
+        assert n == lib.pgnn_chem_gin_num_params(self.L)
+        off = (_ct.c_int64 * (n + 1))()
+        check(lib.pgnn_chem_gin_grad_offsets(self.L, self.D, off), "chem_gin_grad_offsets")
+        self.offsets = list(off)
+        self.sizes = [self.offsets[i + 1] - self.offsets[i] for i in range(n)]
+        self.shapes = [tuple(p.shape) for p in ps]
+        for p, s in zip(ps, self.sizes):
+            if p.numel() != s:
+                raise PgnnError("parameter shape does not match the chem GIN layout (emb_dim / vocabulary sizes)")
+        self.total = self.offsets[-1]
+        self.PtrArr = _ct.c_void_p * n
+        self.BnArr = _ct.c_void_p * self.L
+        self.bns = list(gnn.batch_norms)
+        self.last_flat_grad = None  # the flat gradient buffer of the most recent backward (all-reduce target)
+
+
+class _ChemGinEncoder(Function):
+    @staticmethod
+    def forward(ctx, plan, x, edge_index, edge_attr, training, *params):
+        _dev(x, edge_index, edge_attr, *params)
+        if x.dtype != torch.int64 or x.dim() != 2 or x.shape[1] != 2:
+            raise PgnnError("chem node features must be int64 [N, 2]")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise PgnnError("edge_index must be int64 [2, E]")
+        x, ei, ea = x.contiguous(), edge_index.contiguous(), edge_attr.contiguous()
+        N, E, L, D = x.shape[0], ei.shape[1], plan.L, plan.D
+        if ea.dtype != torch.int64 or tuple(ea.shape) != (E, 2):
+            raise PgnnError("chem edge_attr must be int64 [E, 2]")
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise PgnnError("the fused encoder needs contiguous fp32 parameters")
+        if training and N == 0:
+            raise PgnnError("BatchNorm in training mode needs at least one node")
+        dev = x.device
+        ptrs = plan.PtrArr(*[p.data_ptr() for p in params])
+        bns = plan.bns
+        rm = plan.BnArr(*[b.running_mean.data_ptr() for b in bns])
+        rv = plan.BnArr(*[b.running_var.data_ptr() for b in bns])
+        nbt = plan.BnArr(*[b.num_batches_tracked.data_ptr() for b in bns])
+        wsb = lib.pgnn_chem_gin_workspace_bytes(N, E, L, D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        out = torch.empty(N, D, dtype=torch.float32, device=dev)
+        mom = bns[0].momentum if bns[0].momentum is not None else 0.1
+        check(lib.pgnn_chem_gin_forward(ptrs, rm, rv, nbt, _p(x), _p(ei), _p(ea), N, E, L, D, int(training), float(mom),
+                                        float(bns[0].eps), _precision, _p(out), D, _p(ws), wsb, _st()), "chem_gin_forward")
+        ctx.plan, ctx.ws, ctx.wsb, ctx.ptrs, ctx.x, ctx.dims, ctx.training = plan, ws, wsb, ptrs, x, (N, E, L, D), training
+        ctx.keep = params  # the pointer table refers to these storages
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.training:
+            raise PgnnError("backward through the eval-mode encoder is not implemented (SURVEY.md section 3.3)")
+        plan = ctx.plan
+        N, E, L, D = ctx.dims
+        g = _f32(g)
+        flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_chem_gin_backward(ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), N, E, L, D, _precision, _p(flat), _p(ctx.ws),
+                                         ctx.wsb, _st()), "chem_gin_backward")
+        plan.last_flat_grad = flat
+        grads = [v if len(s) == 1 else v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)]
+        return (None, None, None, None, None) + tuple(gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[5:]))
+
+
+def chem_gin_encoder(plan: ChemGinPlan, x, edge_index, edge_attr, training: bool):
+    return _ChemGinEncoder.apply(plan, x, edge_index, edge_attr, training, *plan.params)

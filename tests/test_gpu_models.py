@@ -42,9 +42,10 @@ def _dev(b):
     return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
 
 
-def _run(domain, t, b, P, training):
+def _run(domain, t, b, P, training, fused=True):
     mod = chem if domain == "chem" else bio
     model = mod.GNN(5, 300, JK="last", drop_ratio=0, gnn_type=t)
+    model.fused = fused
     model.load_state_dict(P)
     model.to(DEV).train(training)
     d = _dev(b)
@@ -65,6 +66,42 @@ def test_module_matches_reference_golden(domain, t):
     stats = {k: v.cpu() for k, v in model.state_dict().items()}
     bad = check_against_golden(G, out_eval.cpu(), out_train.detach().cpu(), grads, stats)
     assert not bad, bad
+
+
+def test_fused_and_layerwise_gin_paths_agree():
+    """GNN.forward binds to the whole-encoder kernels for GIN; the layer-by-layer composition of the same
+    C-ABI operators (model.fused = False) must give the same numbers (same kernels, BN applied on load vs
+    materialised: only rounding differs)."""
+    b = syn.zinc_batch(32, 100)
+    P = O.make_params("chem", "gin", 5, 300, seed=21)
+    R = probe((b["x"].shape[0], 300), 5).to(DEV)
+    res = []
+    for fused in (True, False):
+        model, out = _run("chem", "gin", b, P, True, fused=fused)
+        (out * R).sum().backward()
+        res.append((out.detach(), {k: p.grad for k, p in model.named_parameters()}, model.state_dict()))
+    assert torch.allclose(res[0][0], res[1][0], atol=2e-5, rtol=1e-5)
+    for k in res[0][2]:
+        assert torch.allclose(res[0][2][k].float(), res[1][2][k].float(), atol=1e-5, rtol=1e-5), k
+    with torch.no_grad():
+        _, e1 = _run("chem", "gin", b, P, False, fused=True)
+        _, e2 = _run("chem", "gin", b, P, False, fused=False)
+    assert torch.allclose(e1, e2, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_gin_encoder_vs_oracle_both_paths(fused):
+    b = syn.zinc_batch(32, 100)
+    P = O.make_params("chem", "gin", 5, 300, seed=21)
+    R = probe((b["x"].shape[0], 300), 5)
+    ref_t = O.chem_gnn(P, b["x"], b["edge_index"], b["edge_attr"], 5, "gin", True)
+    g32, g64, floor = _oracle_grads(
+        lambda L: (O.chem_gnn(L, b["x"], b["edge_index"], b["edge_attr"], 5, "gin", True) * R.to(L["x_embedding1.weight"].dtype)).sum(), P)
+    model, out_t = _run("chem", "gin", b, P, True, fused=fused)
+    (out_t * R.to(DEV)).sum().backward()
+    err = (out_t.detach().cpu() - ref_t).abs()
+    assert bool((err <= 1e-4 + 1e-4 * ref_t.abs()).all()), err.max()
+    _check_grads(model.named_parameters(), g32, g64, floor)
 
 
 @pytest.mark.parametrize("t", IMPLEMENTED)
