@@ -144,7 +144,7 @@ PGNN_API int pgnn_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, in
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm1d (chem/model.py:252,269; bio/model.py:24), eps 1e-5, momentum 0.1 passed explicitly.
- * Statistics are accumulated in fp64 (deterministic two-stage reduction, no atomics).
+ * Statistics are accumulated in fp64 (block partials folded with fp64 atomics: order effects ~1e-16).
  * ------------------------------------------------------------------------------------------- */
 PGNN_API int64_t pgnn_bn_workspace_bytes(int64_t M, int64_t C);
 /* train: batch statistics (biased var), y = act((x-mean)*invstd*gamma+beta); save_mean/save_invstd [C]

@@ -143,33 +143,42 @@ k_aggregate_bwd(const float* __restrict__ g, int64_t ldg, int64_t n, int C4, con
   }
 }
 
-// gT[q][c] = sum_i S[i][q] * g[i][g_off + c].  grid.x = row chunks, grid.y = 128-column tiles; each
-// thread owns one column and Q register accumulators, S rows are staged in shared memory; one fp32
-// atomicAdd per (chunk, q, c) folds the chunks.
-constexpr int kTblRows = 128;
+// gT[q][c] = sum_i S[i][q] * g[i][g_off + c].  Blocks of 32 columns x 8 row-lanes sweep 256 rows with
+// coalesced 128-byte loads; each thread keeps Q register accumulators (S rows are warp-broadcast loads), the 8
+// row-lanes are folded in shared memory and one fp32 atomicAdd per (block, q, c) folds the row chunks.
+constexpr int kTblRows = 256;
 constexpr int kMaxQ = 16;
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g, int64_t ldg, int64_t g_off, int64_t n,
                  int C, float* __restrict__ gT, int64_t ldt, float* __restrict__ gT2, int q_split) {
-  __shared__ float s_S[kTblRows * kMaxQ];
+  __shared__ float red[8][kMaxQ][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + lane;
   const int64_t r0 = (int64_t)blockIdx.x * kTblRows;
-  const int rows = (int)((n - r0) < kTblRows ? (n - r0) : kTblRows);
-  for (int t = threadIdx.x; t < rows * Q; t += blockDim.x) s_S[t] = S[r0 * Q + t];
-  __syncthreads();
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= C) return;
+  const int64_t r1 = (r0 + kTblRows < n) ? r0 + kTblRows : n;
   float acc[kMaxQ];
 #pragma unroll
   for (int q = 0; q < kMaxQ; ++q) acc[q] = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float v = g[(r0 + r) * ldg + g_off + c];
+  if (c < C) {
+#pragma unroll 2
+    for (int64_t r = r0 + w; r < r1; r += 8) {
+      const float v = g[r * ldg + g_off + c];
+      const float* s = S + r * Q;
 #pragma unroll
-    for (int q = 0; q < kMaxQ; ++q)
-      if (q < Q) acc[q] = fmaf(s_S[r * Q + q], v, acc[q]);
+      for (int q = 0; q < kMaxQ; ++q)
+        if (q < Q) acc[q] = fmaf(s[q], v, acc[q]);
+    }
   }
 #pragma unroll
-  for (int q = 0; q < kMaxQ; ++q)
-    if (q < Q) atomicAdd(q < q_split ? &gT[(int64_t)q * ldt + c] : &gT2[(int64_t)(q - q_split) * ldt + c], acc[q]);
+  for (int q = 0; q < kMaxQ; ++q) red[w][q][lane] = acc[q];
+  __syncthreads();
+  // 256 threads fold (q, lane) pairs: thread t -> q = t / 32 (+8), lane = t % 32
+  for (int q = w; q < Q; q += 8) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][q][lane];
+    if (c < C) atomicAdd(q < q_split ? &gT[(int64_t)q * ldt + c] : &gT2[(int64_t)(q - q_split) * ldt + c], t);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -241,8 +250,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st) {
   if (n == 0) return PGNN_OK;
-  dim3 grid((unsigned)ceil_div(n, kTblRows), (unsigned)ceil_div(C, 128));
-  k_edge_table_bwd<<<grid, 128, 0, st>>>(S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split);
+  dim3 grid((unsigned)ceil_div(n, kTblRows), (unsigned)ceil_div(C, 32));
+  k_edge_table_bwd<<<grid, 256, 0, st>>>(S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split);
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -1,43 +1,47 @@
 // Dense node transforms on the 5th-generation tensor cores (precision 1): error-compensated 3xTF32.
 //
 // fp32 parity (1e-4, north_star) rules out plain TF32 (10-bit mantissa over K = 300/600).  Every fp32
-// operand x is split in registers into hi = tf32(x) and lo = tf32(x - hi) (cvt.rna), both halves are
-// staged in shared memory, and each k-step issues three tcgen05.mma (lo*hi, hi*lo, hi*hi) into one fp32
-// TMEM accumulator: the dropped lo*lo term and the rounding of lo are ~2^-22 relative, i.e. fp32-class.
+// operand x is used as hi = the raw fp32 word (the tensor core reads its top 19 bits, i.e. truncates to
+// tf32) and lo = x - trunc_tf32(x) (exact in fp32); each k-step issues three tcgen05.mma (lo*hi, hi*lo,
+// hi*hi).  The dropped lo*lo term and the truncation of lo are ~2^-20 relative; measured GEMM error is
+// 1-3e-6 of the output scale, the same class as an fp32 FFMA GEMM (tools/check_tc.py).
 //
 // One kernel template serves the three operand layouts of dense.cu (same roles, same epilogues):
 //   fwd    y[M,N]  = x[M,K]  . w[N,K]^T      A K-major,  B K-major
 //   dgrad  gx[M,K] = gy[M,N] . w[N,K]        A K-major,  B MN-major (w rows are the reduction)
 //   wgrad  gw[N,K] = gy[M,N]^T . x[M,K]      A MN-major, B MN-major (node rows are the reduction; split-K)
 //
-// Structure (per CTA: one 128 x BN output tile, 256 threads):
-//   * operands are converted + written to smem by all threads in the UMMA canonical NO-SWIZZLE layouts
-//     (8x16B core matrices; K-major: rows 16 B apart, MN-major: k 16 B apart), two stages;
-//   * fence.proxy.async + __syncthreads hands a stage to the tensor core; one elected thread issues the
-//     4 k-steps x 3 products and tcgen05.commit's onto that stage's mbarrier, which the writers of the
-//     stage after next wait on -> loads/splits of block k+1 overlap the MMAs of block k;
-//   * epilogue: tcgen05.ld (32 lanes x 16 columns per warp and step) -> bias / ReLU / mask -> global.
-// TMA is not used for the operands because the hi/lo split has to happen between global and shared
-// memory; the fused layer kernel reuses this staging code with the gather as its A producer.
+// Structure (per CTA: one 128 x BN output tile; 8 producer warps + 1 MMA warp; 4 smem stages of BK = 16):
+//   * producers cp.async (16 B, L2-only, zero-filled out of bounds) the raw fp32 operand pieces straight into
+//     the UMMA canonical smem layouts (K-major: no-swizzle 8x16B core matrices; MN-major: 128B swizzle with
+//     32B base, the only layout tf32 accepts transposed), two blocks ahead; when a thread's own pieces of a
+//     block have landed (cp.async.wait_group) it re-reads them, writes lo into the stage's second buffer,
+//     fence.proxy.async's, and its warp arrives on full[stage];
+//   * the MMA warp waits full[stage], one lane issues 2 k-steps x 3 products and tcgen05.commit's onto
+//     empty[stage]; the hi*hi chain and the cross terms use separate TMEM accumulators (truncating adds);
+//   * epilogue (producer warps): tcgen05.ld both accumulators -> add -> bias / ReLU / mask -> global.
+// No block-wide barrier and no register-staged global load sits in the main loop: the only waits are
+// the two mbarrier rings and the thread's own cp.async group.
 #include "common.cuh"
 
 namespace {
 
 constexpr int BM = 128;       // UMMA M (TMEM lanes)
-constexpr int BK = 32;        // fp32 elements of the reduction per stage = 4 UMMA k-steps of 8
-constexpr int NTHREADS = 256;
-constexpr int NSTAGE = 2;
+constexpr int BK = 16;        // fp32 elements of the reduction per stage = 2 UMMA k-steps of 8
+constexpr int NPRODUCER = 256;  // 8 producer warps (they also run the epilogue)
+constexpr int NTHREADS = NPRODUCER + 32;  // + one MMA-issuing warp
+constexpr int NSTAGE = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // byte sizes of one operand buffer (hi or lo) for a tile of R rows (MN extent) x BK
-__host__ __device__ constexpr int kmajor_lbo(int R) { return R * 16 + 16; }          // stride between 16-byte k-chunks (+16: the 8 chunks of a row hit 8 distinct bank groups)
+__host__ __device__ constexpr int kmajor_lbo(int R) { return R * 16 + 32; }          // stride between 16-byte k-chunks (+32: a quarter-warp = 2 rows x 4 chunks hits 8 distinct bank groups)
 __host__ __device__ constexpr int kmajor_bytes(int R) { return kmajor_lbo(R) * (BK / 4); }
 // MN-major tf32 operands must use the 128B-swizzle-with-32B-base layout (UMMA layout type 1): atoms of
 // [4 k][32 consecutive row indices] = 4 rows of 128 B, the 32-byte chunk index XOR-ed with (k mod 4).
 // A tile keeps the BK/4 atoms of one 32-row block contiguous: k-group stride (SBO) 512 B, block stride (LBO) 4 KiB.
 constexpr int MN_SBO = 512;
-constexpr int MN_LBO = (BK / 4) * MN_SBO;
+constexpr int MN_LBO = (BK / 4) * MN_SBO;  // 2 KiB at BK = 16
 __host__ __device__ constexpr int mnmajor_bytes(int R) { return (R / 32) * MN_LBO; }
 
 // UMMA shared-memory matrix descriptor, version 1 (sm_100).
@@ -66,6 +70,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -116,12 +123,24 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// hi = tf32(x) rounded to nearest; lo = x - hi is exact in fp32 (|lo| <= 2^-11 |x|) and is left unrounded: the
+// tensor core reads only its top 19 bits, an error of 2^-10 |lo| <= 2^-21 |x|, the same order as the dropped lo*lo.
 __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
+#ifdef PGNN_TRUNC_SPLIT
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+#else
   hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-  lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+#endif
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 
-__device__ int g_tc_mn_variant = 0;  // development switch for the MN-major descriptor convention
+// development trace: globaltimer stamps of CTA (0,0,0) at the phase boundaries (pgnn_debug_tc_trace reads it)
+__device__ unsigned long long g_tc_trace[16];
+#define TC_TRACE(slot)                                                                        \
+  do {                                                                                        \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) g_tc_trace[slot] = globaltimer_ns(); \
+  } while (0)
 
 struct TcEpilogue {
   const float* bias;      // [N] or null
@@ -131,61 +150,73 @@ struct TcEpilogue {
   int atomic;             // split-K: accumulate with atomics into a zeroed output
 };
 
-// Operand tile loader.  KC: source is contiguous along the reduction (element (r,k) at src[r*ld + k]);
-// otherwise contiguous along the row index (element (r,k) at src[k*ld + r]).  R = rows in the tile.
-// Each thread owns NV float4 vectors; `fetch` pulls them from global (zero-filled out of bounds),
-// `stash` splits them and writes hi/lo into the canonical smem layout.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Operand tile.  KC: source is contiguous along the reduction (element (r,k) at src[r*ld + k]); otherwise
+// contiguous along the row index (element (r,k) at src[k*ld + r]).  R = rows (MN extent) of the tile.
+// Each producer thread owns NV 16-byte pieces per block, the same ones in `issue` (cp.async raw -> smem)
+// and in `make_lo` (re-read own pieces, write x - trunc_tf32(x)).
 template <bool KC, int R>
 struct Operand {
   static constexpr int VEC = R * BK / 4;
-  static constexpr int NV = (VEC + NTHREADS - 1) / NTHREADS;
+  static constexpr int NV = (VEC + NPRODUCER - 1) / NPRODUCER;
   // rounded to 1 KiB so that every buffer (the swizzled MN-major ones need 512 B atoms) starts aligned
   static constexpr int BYTES = ((KC ? kmajor_bytes(R) : mnmajor_bytes(R)) + 1023) / 1024 * 1024;
-  float4 v[NV];
 
-  __device__ __forceinline__ void fetch(const float* __restrict__ src, int64_t ld, int r0, int rows, int k0, int kend) {
+  __device__ __forceinline__ static int smem_off(int f) {
+    if (KC) {
+      const int r = f / (BK / 4), kc = f % (BK / 4);
+      return kc * kmajor_lbo(R) + (r >> 3) * 128 + (r & 7) * 16;
+    }
+    const int k = f / (R / 4), rc = f % (R / 4);  // rc: group of 4 consecutive row indices
+    return (rc >> 3) * MN_LBO + (k >> 2) * MN_SBO + (k & 3) * 128 + ((((rc >> 1) & 3) ^ (k & 3)) << 5) + (rc & 1) * 16;
+  }
+  __device__ __forceinline__ static void issue(const float* __restrict__ src, int64_t ld, int r0, int rows, int k0, int kend,
+                                               uint8_t* raw) {
+    const uint32_t base = smem_u32(raw);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int f = threadIdx.x + i * NTHREADS;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int f = threadIdx.x + i * NPRODUCER;
       if (f < VEC) {
+        const float* g = src;
+        uint32_t bytes = 0;
         if (KC) {
           const int r = f / (BK / 4), kc = f % (BK / 4);
           const int gr = r0 + r, gk = k0 + kc * 4;
-          if (gr < rows && gk < kend) t = *reinterpret_cast<const float4*>(src + (int64_t)gr * ld + gk);  // kend % 4 == 0
+          if (gr < rows && gk < kend) { g = src + (int64_t)gr * ld + gk; bytes = 16; }   // kend % 4 == 0
         } else {
           const int k = f / (R / 4), rc = f % (R / 4);
           const int gk = k0 + k, gr = r0 + rc * 4;
-          if (gk < kend && gr < rows) t = *reinterpret_cast<const float4*>(src + (int64_t)gk * ld + gr);  // rows % 4 == 0
+          if (gk < kend && gr < rows) { g = src + (int64_t)gk * ld + gr; bytes = 16; }   // rows % 4 == 0
         }
+        cp_async16(base + smem_off(f), g, bytes);  // bytes == 0: the 16 B are zero-filled
       }
-      v[i] = t;
     }
   }
-  __device__ __forceinline__ void stash(uint8_t* hi_buf, uint8_t* lo_buf) const {
+  __device__ __forceinline__ static void make_lo(const uint8_t* raw, uint8_t* lo) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int f = threadIdx.x + i * NTHREADS;
+      const int f = threadIdx.x + i * NPRODUCER;
       if (f < VEC) {
-        int off;
-        if (KC) {
-          const int r = f / (BK / 4), kc = f % (BK / 4);
-          off = kc * kmajor_lbo(R) + (r >> 3) * 128 + (r & 7) * 16;
-        } else {
-          const int k = f / (R / 4), rc = f % (R / 4);  // rc: group of 4 consecutive row indices
-          off = (rc >> 3) * MN_LBO + (k >> 2) * MN_SBO + (k & 3) * 128 + ((((rc >> 1) & 3) ^ (k & 3)) << 5) + (rc & 1) * 16;
-        }
-        float4 hi, lo;
-        split4(v[i], hi, lo);
-        *reinterpret_cast<float4*>(hi_buf + off) = hi;
-        *reinterpret_cast<float4*>(lo_buf + off) = lo;
+        const int off = smem_off(f);
+        const float4 v = *reinterpret_cast<const float4*>(raw + off);
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        *reinterpret_cast<float4*>(lo + off) = l;
       }
     }
   }
   // descriptor of k-step j (8 reduction elements) inside a staged buffer
   __device__ __forceinline__ static uint64_t desc(uint32_t base, int j) {
     if (KC) return umma_desc(base + 2 * j * kmajor_lbo(R), kmajor_lbo(R), 128);
-    if (g_tc_mn_variant == 1) return umma_desc(base + j * 2 * MN_SBO, MN_SBO, MN_LBO, 1);
     return umma_desc(base + j * 2 * MN_SBO, MN_LBO, MN_SBO, 1);  // k-step = 8 k = two 4-deep atoms
   }
 };
@@ -201,6 +232,10 @@ template <bool A_KC, bool B_KC, int BN>
 __host__ __device__ constexpr int smem_bytes() { return NSTAGE * 2 * (Operand<A_KC, BM>::BYTES + Operand<B_KC, BN>::BYTES) + 1024; }
 
 // C[m, n] = sum_r A(m, r) * B(n, r) over r in [kbeg, kend) of this split.
+// Warp roles: warps 0..7 = producers (global -> registers -> hi/lo split -> smem stage, then the epilogue),
+// warp 8 = MMA issuer.  Stages are handed over with mbarriers only (full[s]: 8 producer-warp arrivals,
+// empty[s]: tcgen05.commit), so producers run up to NSTAGE blocks ahead of the tensor core and no block-wide
+// barrier sits in the main loop.
 template <bool A_KC, bool B_KC, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
@@ -208,8 +243,9 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   using OpA = Operand<A_KC, BM>;
   using OpB = Operand<B_KC, BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mma_done[NSTAGE];
+  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[BN];  // this tile's bias slice (zero past N), loaded once at the prologue
 
   uint8_t* bufs = smem;
   auto a_hi = [&](int s) { return bufs + s * 2 * (OpA::BYTES + OpB::BYTES); };
@@ -222,6 +258,9 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   const int kbeg = blockIdx.z * k_per_split;
   const int kend = min(K, kbeg + k_per_split);
   const int nkb = (kend - kbeg + BK - 1) / BK;
+  if (warp == 0) TC_TRACE(0);
+  const bool s_bias_on = ep.bias != nullptr && blockIdx.z == 0;
+  for (int i = threadIdx.x; i < BN; i += NTHREADS) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -230,7 +269,11 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 32) {
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(smem_u32(&mma_done[s]), 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), NPRODUCER / 32);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&acc_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -238,32 +281,46 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
   constexpr uint32_t idesc = umma_idesc(BM, BN, !A_KC, !B_KC);
+  if (warp == 0) TC_TRACE(1);
 
-  // Register double-buffering: the global loads of block kb+2 are issued before block kb+1 is split, so a
-  // load has two block-times (2 x 12 MMAs) to arrive and HBM/L2 latency stays off the critical path.
-  OpA ra[2];
-  OpB rb[2];
-  if (nkb > 0) {
-    ra[0].fetch(A, lda, m0, M, kbeg, kend);
-    rb[0].fetch(B, ldb, n0, N, kbeg, kend);
-  }
-  if (nkb > 1) {
-    ra[1].fetch(A, lda, m0, M, kbeg + BK, kend);
-    rb[1].fetch(B, ldb, n0, N, kbeg + BK, kend);
-  }
-  auto block = [&](int kb, OpA& qa, OpB& qb) {
-    const int s = kb & 1;
-    if (kb >= NSTAGE) mbar_wait(smem_u32(&mma_done[s]), ((kb / NSTAGE) - 1) & 1);  // MMAs of block kb-2 released stage s
-    qa.stash(a_hi(s), a_lo(s));
-    qb.stash(b_hi(s), b_lo(s));
-    if (kb + 2 < nkb) {
-      qa.fetch(A, lda, m0, M, kbeg + (kb + 2) * BK, kend);
-      qb.fetch(B, ldb, n0, N, kbeg + (kb + 2) * BK, kend);
+  if (warp < NPRODUCER / 32) {
+    // ---------------- producers ----------------
+    // block kb: wait for its stage, cp.async the raw pieces (they double as the hi operand); then finish block
+    // kb-AHEAD: its cp.async group has landed, derive lo from this thread's own pieces and publish the stage.
+    constexpr int AHEAD = 2;
+    auto publish = [&](int kb) {
+      const int s = kb % NSTAGE;
+      OpA::make_lo(a_hi(s), a_lo(s));
+      OpB::make_lo(b_hi(s), b_lo(s));
+      fence_async_smem();  // cp.async-written raw tiles + the lo stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+    };
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NSTAGE;
+      if (kb >= NSTAGE) mbar_wait(smem_u32(&empty_bar[s]), ((kb / NSTAGE) - 1) & 1);  // MMAs of block kb-NSTAGE are done
+      OpA::issue(A, lda, m0, M, kbeg + kb * BK, kend, a_hi(s));
+      OpB::issue(B, ldb, n0, N, kbeg + kb * BK, kend, b_hi(s));
+      cp_async_commit();
+      if (kb >= AHEAD) {
+        cp_async_wait<AHEAD>();  // all but the newest AHEAD groups are complete -> block kb-AHEAD has landed
+        publish(kb - AHEAD);
+        if (warp == 0 && kb == AHEAD) TC_TRACE(2);  // first block published
+      }
     }
-    fence_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (warp == 0) {
+    cp_async_wait<0>();
+    for (int kb = (nkb > AHEAD ? nkb - AHEAD : 0); kb < nkb; ++kb) publish(kb);
+    if (warp == 0) TC_TRACE(3);  // last block published
+  } else {
+    // ---------------- MMA issuer ----------------
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % NSTAGE;
+      mbar_wait(smem_u32(&full_bar[s]), (kb / NSTAGE) & 1);
       tc_fence_after();
+      if (kb == 0) TC_TRACE(4);        // MMA warp: first stage ready
+      if (kb == nkb - 1) TC_TRACE(5);  // MMA warp: last stage ready
       if (lane == 0) {
         const uint32_t ah = smem_u32(a_hi(s)), al = smem_u32(a_lo(s)), bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
 #pragma unroll
@@ -273,82 +330,141 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
           umma_tf32(tmem_acc + BN, OpA::desc(ah, j), OpB::desc(bl, j), idesc, 1u);
           umma_tf32(tmem_acc, OpA::desc(ah, j), OpB::desc(bh, j), idesc, first);
         }
-        umma_commit(smem_u32(&mma_done[s]));  // implies tcgen05.fence::before_thread_sync
+        umma_commit(smem_u32(&empty_bar[s]));           // stage s is free once these MMAs have read it
+        if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));  // accumulators complete
       }
       __syncwarp();
     }
-  };
-  for (int kb = 0; kb < nkb; kb += 2) {  // unrolled by two so the register sets are addressed statically
-    block(kb, ra[0], rb[0]);
-    if (kb + 1 < nkb) block(kb + 1, ra[1], rb[1]);
   }
-  if (nkb > 0) {
-    const int last = nkb - 1;
-    mbar_wait(smem_u32(&mma_done[last & 1]), (last / NSTAGE) & 1);  // the last commit covers every earlier MMA
+  if (warp >= NPRODUCER / 32) {
+    // the MMA warp only has to stay alive until TMEM is released
+    tc_fence_before();
+    __syncthreads();
+    return;
   }
+  if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
   tc_fence_after();
+  if (warp == 0) TC_TRACE(6);  // accumulators complete, epilogue starts
 
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4 ----
-  const int row = (warp & 3) * 32 + lane;
-  const int gm = m0 + row;
-  const int cbeg = (warp >> 2) * (BN / 2);
+  // ---- epilogue ----
+  // (1) TMEM -> registers -> smem staging tile [128][BN+4] (the operand stages are free: every MMA has
+  //     completed).  Warp w owns TMEM lanes 32*(w%4).., column half w/4; both accumulators are summed here.
+  // (2) the 8 warps write the tile out row-contiguously (a warp instruction covers 512 consecutive bytes of
+  //     one output row), applying bias / ReLU / mask on the way.  Writing straight from the TMEM register
+  //     layout (one row per lane) would issue 16-byte stores to 32 different rows per instruction.
+  constexpr int SLD = BN + 4;  // staging row stride in floats: 16 B aligned, quarter-warps hit distinct banks
+  float* stage = reinterpret_cast<float*>(smem);
+  {
+    const int row = (warp & 3) * 32 + lane;
+    const int cbeg = (warp >> 2) * (BN / 2);
 #pragma unroll 1
-  for (int c = 0; c < BN / 2; c += 16) {
-    float v[16];
-    if (nkb > 0) {
-      float x[16];
-      tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbeg + c), v);
-      tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + cbeg + c), x);
+    for (int c = 0; c < BN / 2; c += 16) {
+      float v[16];
+      if (nkb > 0) {
+        float x[16];
+        tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbeg + c), v);
+        tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + cbeg + c), x);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += x[i];
-    } else {
+        for (int i = 0; i < 16; ++i) v[i] += x[i];
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      float* dst = stage + row * SLD + cbeg + c;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
-    const int gn0 = n0 + cbeg + c;
-    if (gm < M && gn0 < N) {
+  }
+  if (warp == 0) TC_TRACE(9);
+  // only the producer warps take part from here on (the MMA warp has left through its own barrier below)
+  asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
+  {
+    constexpr int C4 = BN / 4;
+    constexpr int UNR = 4;  // independent row pieces per thread and trip: keeps the mask loads in flight together
+    const int rows_here = min(BM, M - m0);
+    const int total = rows_here * C4;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool mvec_ok = ep.mask_src && ((ep.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask_src) & 15) == 0);
+    for (int base = threadIdx.x; base < total; base += NPRODUCER * UNR) {
+      float4 o[UNR], mk[UNR];
+      int gm[UNR], gn[UNR];
+      bool live[UNR];
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const int gn = gn0 + i;
-        if (gn >= N) break;
-        float o[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (gn + q < N) {
-            if (ep.bias && blockIdx.z == 0) o[q] += ep.bias[gn + q];
-            if (ep.relu) o[q] = fmaxf(o[q], 0.f);
-            if (ep.mask_src) o[q] = ep.mask_src[(int64_t)gm * ep.ldm + gn + q] > 0.f ? o[q] : 0.f;
+      for (int u = 0; u < UNR; ++u) {
+        const int idx = base + u * NPRODUCER;
+        const int r = idx / C4, c4 = idx - r * C4;
+        gm[u] = m0 + r;
+        gn[u] = n0 + c4 * 4;
+        live[u] = idx < total && gn[u] < N;
+        mk[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (live[u]) {
+          o[u] = *reinterpret_cast<const float4*>(stage + r * SLD + c4 * 4);
+          if (ep.mask_src) {
+            const float* mp = ep.mask_src + (int64_t)gm[u] * ep.ldm + gn[u];
+            if (mvec_ok && gn[u] + 3 < N) mk[u] = *reinterpret_cast<const float4*>(mp);
+            else {
+              mk[u].x = mp[0];
+              mk[u].y = gn[u] + 1 < N ? mp[1] : 1.f;
+              mk[u].z = gn[u] + 2 < N ? mp[2] : 1.f;
+              mk[u].w = gn[u] + 3 < N ? mp[3] : 1.f;
+            }
           }
         }
-        float* dst = C + (int64_t)gm * ldc + gn;
-        if (gn + 3 < N && ((ldc & 3) == 0)) {
-          if (ep.atomic) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
-          else *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (!live[u]) continue;
+        float ov[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
+        const float mv[4] = {mk[u].x, mk[u].y, mk[u].z, mk[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (s_bias_on) ov[q] += s_bias[gn[u] - n0 + q];
+          if (ep.relu) ov[q] = fmaxf(ov[q], 0.f);
+          ov[q] = mv[q] > 0.f ? ov[q] : 0.f;
+        }
+        float* dst = C + (int64_t)gm[u] * ldc + gn[u];
+        if (gn[u] + 3 < N && vec_ok) {
+          if (ep.atomic) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(ov[0], ov[1], ov[2], ov[3]));
+          else *reinterpret_cast<float4*>(dst) = make_float4(ov[0], ov[1], ov[2], ov[3]);
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (gn + q < N) {
-              if (ep.atomic) atomicAdd(dst + q, o[q]); else dst[q] = o[q];
+            if (gn[u] + q < N) {
+              if (ep.atomic) atomicAdd(dst + q, ov[q]); else dst[q] = ov[q];
             }
         }
       }
     }
   }
+  if (warp == 0) TC_TRACE(7);  // warp 0 epilogue done
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) TC_TRACE(8);  // all epilogue warps done
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_colsum_tc(const float* __restrict__ gy, int64_t ld, int M, int N, int rows_per_split, float* __restrict__ gb) {
-  const int n = blockIdx.x * 128 + threadIdx.x;
-  if (n >= N) return;
-  const int r0 = blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
+// gb[n] = sum_m gy[m][n]: 32 columns x 8 row-lanes per block, coalesced row sweeps, smem fold, one atomic per column
+__global__ void __launch_bounds__(256)
+k_colsum_tc(const float* __restrict__ gy, int64_t ld, int M, int N, int rows_per_block, float* __restrict__ gb) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float a = 0.f;
-  for (int r = r0; r < r1; ++r) a += gy[(int64_t)r * ld + n];
-  atomicAdd(&gb[n], a);
+  if (n < N) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) a += gy[(int64_t)r * ld + n];
+  }
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    atomicAdd(&gb[n], t);
+  }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -368,17 +484,17 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, i
   return PGNN_OK;
 }
 
-// Tile width: the candidate that minimises (waves over 148 SMs) x (tile width), i.e. the tensor time of the slowest SM.
+// Tile width.  Every CTA re-reads its 128 x K slab of A and its BN x K slab of B from L2, so narrow tiles
+// multiply operand traffic (measured: the main loop runs at the ~3 TB/s the L2 delivers to 16-byte cp.async
+// requests, not at tensor speed).  Take the widest candidate whose padding waste stays under ~15%.
 inline int pick_bn(int M, int N, int splits) {
-  const int cand[4] = {64, 128, 160, 224};
-  int best = 64;
-  double best_cost = 1e30;
+  (void)M; (void)splits;
+  const int cand[4] = {224, 160, 128, 64};
   for (int bn : cand) {
-    const int64_t tiles = ceil_div(M, BM) * ceil_div(N, bn) * splits;
-    const double cost = (double)ceil_div(tiles, kNumSMs) * (bn + 48);  // +48: per-tile fixed cost (prologue/epilogue)
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    const int padded = (int)ceil_div(N, bn) * bn;
+    if (padded <= N + N * 15 / 100 || bn == 64) return bn;
   }
-  return best;
+  return 64;
 }
 
 template <bool A_KC, bool B_KC>
@@ -394,8 +510,8 @@ int dispatch(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, f
 
 }  // namespace
 
-extern "C" __attribute__((visibility("default"))) int pgnn_debug_set_tc_variant(int v) {
-  return cudaMemcpyToSymbol(g_tc_mn_variant, &v, sizeof(int)) == cudaSuccess ? 0 : -2;
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_tc_trace(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
 }
 
 // development entry: C[M,N] = sum_r A(m,r) B(n,r) with explicit operand majors (1 = reduction-contiguous)
@@ -448,11 +564,9 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
   if (rc != PGNN_OK) return rc;
   if (gb) {
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
-    int rsplit = (int)ceil_div(M, 256);
-    if (rsplit > 64) rsplit = 64;
-    const int rows_per = (int)ceil_div(M, rsplit);
-    dim3 g2((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, rows_per));
-    k_colsum_tc<<<g2, 128, 0, st>>>(gy, ldgy, (int)M, (int)N, rows_per, gb);
+    const int rows_per = 256;
+    dim3 g2((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, rows_per));
+    k_colsum_tc<<<g2, 256, 0, st>>>(gy, ldgy, (int)M, (int)N, rows_per, gb);
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;

@@ -1,54 +1,63 @@
 // BatchNorm1d (chem/model.py:252,269; bio/model.py:24), the inter-layer ReLU (bio/model.py:281) and
 // GraphSAGE's row L2-normalisation (chem/model.py:201-202), forward and backward.
 //
-// Column statistics are a grid-wide dependency.  They are reduced in two deterministic stages:
-// per-(row-chunk, column) partial sums in fp64 -> one finalize pass that walks the chunks in order.
-// fp64 accumulation makes E[x^2]-E[x]^2 safe (relative error ~1e-16 * mean^2/var) and costs nothing
-// measurable at [N<=40k, C<=600].
+// Column statistics are a grid-wide dependency.  Blocks of 32 columns x 8 row-lanes sweep a row chunk with
+// coalesced 128-byte loads, accumulate in fp64, fold the 8 lanes in shared memory and add their partial to
+// the [2, C] accumulators with fp64 atomics (order-dependent only at the 1e-16 level, i.e. invisible in the
+// fp32 results); a finalize pass over the C columns derives mean / invstd / scale / shift.  fp64
+// accumulation makes E[x^2]-E[x]^2 safe (relative error ~1e-16 * mean^2/var).
 #include "common.cuh"
 
 namespace {
 
-constexpr int kMaxChunks = 2 * kNumSMs;  // 296 row chunks at most
+constexpr int kStatRows = 128;  // rows per block of the statistics sweeps
 
-struct Chunking { int chunks, rows_per; };
-inline Chunking chunking(int64_t M) {
-  int64_t chunks = ceil_div(M, 32);
-  if (chunks > kMaxChunks) chunks = kMaxChunks;
-  if (chunks < 1) chunks = 1;
-  const int64_t rows_per = ceil_div(M, chunks);
-  chunks = ceil_div(M, rows_per);
-  return {(int)chunks, (int)rows_per};
-}
-
-__global__ void __launch_bounds__(128)
-k_bn_partial(const float* __restrict__ x, int64_t ldx, int M, int C, int rows_per, double* __restrict__ part) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
-  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  double s = 0.0, ss = 0.0;
-  for (int r = r0; r < r1; ++r) {
-    const double v = (double)x[(int64_t)r * ldx + c];
-    s += v;
-    ss += v * v;
+// sums of f0(row, col) and f1(row, col) over the rows, per column -> acc[0][C], acc[1][C] (fp64 atomics)
+template <typename F>
+__device__ __forceinline__ void column_pair_sums(int M, int C, double* __restrict__ acc, F f) {
+  __shared__ double red[2][8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * kStatRows, r1 = min(M, r0 + kStatRows);
+  double s0 = 0.0, s1 = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      double a, b;
+      f(r, c, a, b);
+      s0 += a;
+      s1 += b;
+    }
   }
-  part[((int64_t)blockIdx.y * 2 + 0) * C + c] = s;
-  part[((int64_t)blockIdx.y * 2 + 1) * C + c] = ss;
+  red[0][w][lane] = s0;
+  red[1][w][lane] = s1;
+  __syncthreads();
+  if (w < 2 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[w][k][lane];
+    atomicAdd(&acc[(int64_t)w * C + c], t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_stats(const float* __restrict__ x, int64_t ldx, int M, int C, double* __restrict__ acc) {
+  column_pair_sums(M, C, acc, [&](int r, int c, double& a, double& b) {
+    const double v = (double)x[(int64_t)r * ldx + c];
+    a = v;
+    b = v * v;
+  });
 }
 
 __global__ void __launch_bounds__(128)
-k_bn_finalize(const double* __restrict__ part, int chunks, int M, int C, const float* __restrict__ gamma,
-              const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
-              int64_t* __restrict__ nbt, float momentum, float eps, float* __restrict__ save_mean,
-              float* __restrict__ save_invstd, float* __restrict__ scale, float* __restrict__ shift) {
+k_bn_finalize(const double* __restrict__ acc, int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ nbt, float momentum,
+              float eps, float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ scale,
+              float* __restrict__ shift) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    s += part[((int64_t)k * 2 + 0) * C + c];
-    ss += part[((int64_t)k * 2 + 1) * C + c];
-  }
+  const double s = acc[c], ss = acc[(int64_t)C + c];
   const double mean = s / M;
   double var = ss / M - mean * mean;
   var = var < 0.0 ? 0.0 : var;
@@ -97,36 +106,25 @@ k_bn_eval(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const floa
   }
 }
 
-__global__ void __launch_bounds__(128)
-k_bn_bwd_partial(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
-                 int rows_per, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                 const float* __restrict__ invstd, int relu, double* __restrict__ part) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
-  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
-  const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
-  double s = 0.0, sx = 0.0;
-  for (int r = r0; r < r1; ++r) {
-    const float xhat = (x[(int64_t)r * ldx + c] - mu) * is;
+__global__ void __launch_bounds__(256)
+k_bn_bwd_stats(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
+               const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+               const float* __restrict__ invstd, int relu, double* __restrict__ acc) {
+  column_pair_sums(M, C, acc, [&](int r, int c, double& a, double& b) {
+    const float xhat = (x[(int64_t)r * ldx + c] - mean[c]) * invstd[c];
     float d = gy[(int64_t)r * ldgy + c];
-    if (relu && !(fmaf(xhat, ga, be) > 0.f)) d = 0.f;
-    s += (double)d;
-    sx += (double)d * (double)xhat;
-  }
-  part[((int64_t)blockIdx.y * 2 + 0) * C + c] = s;
-  part[((int64_t)blockIdx.y * 2 + 1) * C + c] = sx;
+    if (relu && !(fmaf(xhat, gamma[c], beta[c]) > 0.f)) d = 0.f;
+    a = (double)d;
+    b = (double)d * (double)xhat;  // exact product: small batches make the BN backward a difference of large terms
+  });
 }
 
 __global__ void __launch_bounds__(128)
-k_bn_bwd_finalize(const double* __restrict__ part, int chunks, int M, int C, float* __restrict__ ggamma,
-                  float* __restrict__ gbeta, float* __restrict__ c1, float* __restrict__ c2) {
+k_bn_bwd_finalize(const double* __restrict__ acc, int M, int C, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                  float* __restrict__ c1, float* __restrict__ c2) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    s += part[((int64_t)k * 2 + 0) * C + c];
-    sx += part[((int64_t)k * 2 + 1) * C + c];
-  }
+  const double s = acc[c], sx = acc[(int64_t)C + c];
   if (gbeta) gbeta[c] = (float)s;
   if (ggamma) ggamma[c] = (float)sx;
   c1[c] = (float)(s / M);
@@ -214,7 +212,7 @@ extern "C" {
 
 int64_t pgnn_bn_workspace_bytes(int64_t M, int64_t C) {
   if (M < 0 || C <= 0) return PGNN_EINVAL;
-  return align_up((int64_t)kMaxChunks * 2 * C * 8, 256) + align_up(2 * C * 4, 256);
+  return align_up(2 * C * 8, 256) + align_up(2 * C * 4, 256);
 }
 
 int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma, const float* beta,
@@ -225,14 +223,14 @@ int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const f
   PGNN_CHECK_ARG((scale == nullptr) == (shift == nullptr));
   if (workspace_bytes < pgnn_bn_workspace_bytes(M, C)) return PGNN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
-  double* part = reinterpret_cast<double*>(workspace);
-  const Chunking ch = chunking(M);
-  dim3 g1((unsigned)ceil_div(C, 128), (unsigned)ch.chunks);
-  k_bn_partial<<<g1, 128, 0, st>>>(x, ldx, (int)M, (int)C, ch.rows_per, part);
+  double* acc = reinterpret_cast<double*>(workspace);
+  PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
+  dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
+  k_bn_stats<<<g1, 256, 0, st>>>(x, ldx, (int)M, (int)C, acc);
   PGNN_LAUNCH_CHECK();
-  k_bn_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(part, ch.chunks, (int)M, (int)C, gamma, beta, running_mean,
-                                                           running_var, num_batches_tracked, momentum, eps, save_mean,
-                                                           save_invstd, scale, shift);
+  k_bn_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, gamma, beta, running_mean, running_var,
+                                                           num_batches_tracked, momentum, eps, save_mean, save_invstd, scale,
+                                                           shift);
   PGNN_LAUNCH_CHECK();
   if (y) {
     k_bn_apply<<<grid_items(M * C, 256), 256, 0, st>>>(x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy);
@@ -259,15 +257,14 @@ int pgnn_bn_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int6
   PGNN_CHECK_ARG(M > 0 && C > 0 && M < (1ll << 31) && gy && x && gamma && beta && save_mean && save_invstd && gx && workspace);
   if (workspace_bytes < pgnn_bn_workspace_bytes(M, C)) return PGNN_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
-  double* part = reinterpret_cast<double*>(workspace);
-  float* c1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up((int64_t)kMaxChunks * 2 * C * 8, 256));
+  double* acc = reinterpret_cast<double*>(workspace);
+  float* c1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(2 * C * 8, 256));
   float* c2 = c1 + C;
-  const Chunking ch = chunking(M);
-  dim3 g1((unsigned)ceil_div(C, 128), (unsigned)ch.chunks);
-  k_bn_bwd_partial<<<g1, 128, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, ch.rows_per, gamma, beta, save_mean, save_invstd, relu,
-                                       part);
+  PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
+  dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
+  k_bn_bwd_stats<<<g1, 256, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc);
   PGNN_LAUNCH_CHECK();
-  k_bn_bwd_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(part, ch.chunks, (int)M, (int)C, ggamma, gbeta, c1, c2);
+  k_bn_bwd_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, ggamma, gbeta, c1, c2);
   PGNN_LAUNCH_CHECK();
   k_bn_bwd_apply<<<grid_items(M * C, 256), 256, 0, st>>>(gy, ldgy, x, ldx, M, (int)C, gamma, beta, save_mean, save_invstd, relu,
                                                         c1, c2, gx, ldgx);

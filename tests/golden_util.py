@@ -57,8 +57,10 @@ def close_scaled(a, b, tol=1e-4, floor=1.0):
     ReLU-boundary allowance: a hidden pre-activation within rounding distance of 0 lands on the other side
     of the ReLU under a different (equally valid) fp32 summation order; its gradient mask flips and the
     change propagates to every upstream gradient.  With ~10^5-10^6 hidden units per step a handful of such
-    flips is the expected case, not an accident (P ~ units * rounding_error / activation_scale).  They are
-    accepted when at least 90% of the entries are within `tol` and the relative Frobenius error is < 2%."""
+    flips is the expected case, not an accident (P ~ units * rounding_error / activation_scale).  A flip
+    moves a few rows of some gradients by a finite amount but leaves the tensor as a whole where it was, so a
+    tensor that misses the max-norm bound is still accepted when its relative L2 (Frobenius) error is below
+    0.5% -- a wrong formula or a wrong index shows up as O(10%-100%) there."""
     a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
     b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
     if not b.numel():
@@ -69,9 +71,8 @@ def close_scaled(a, b, tol=1e-4, floor=1.0):
     if e <= tol:
         return True, e
     if b.numel() >= 64:
-        frac_ok = float((err <= tol).double().mean().item())
-        fro = float((a - b).norm().item() / max(b.norm().item(), floor))
-        if frac_ok >= 0.90 and fro <= 2e-2:
+        fro = float((a - b).norm().item() / max(b.norm().item(), 1e-30))
+        if fro <= 5e-3:
             return True, e
     return False, e
 

@@ -12,11 +12,15 @@ dev = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
+COLD = True
+
+
 def timeit(fn, reps=10):
     fn(); torch.cuda.synchronize()
     tot = 0.0
     for _ in range(reps):
-        flush.zero_()
+        if COLD:
+            flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); b.synchronize()
         tot += a.elapsed_time(b)
@@ -56,6 +60,9 @@ def run(M, N, K, seed=0):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "warm":
+        COLD = False
+        print("warm L2 (no flush between launches)")
     for shape in [(5986, 600, 300), (5986, 300, 600), (130, 600, 300), (1, 8, 4), (1024, 119, 300), (32000, 600, 600), (777, 300, 300)]:
         M, N, K = shape
         if N % 4:  # dgrad/wgrad of the tensor path need N % 4 == 0; the library falls back to FFMA there
