@@ -16,7 +16,8 @@ from ._cabi import PgnnError, check, lib
 
 AGG_SUM, AGG_MEAN, AGG_GCN = 0, 1, 2
 _PRECISION = {"fp32": 0, "tf32x3": 1}
-_precision = _PRECISION.get(os.environ.get("PGNN_PRECISION", "fp32"), 0)
+# default: the tensor-core path (measured fp32-class accuracy, tools/check_tc.py); PGNN_PRECISION=fp32 forces FFMA
+_precision = _PRECISION.get(os.environ.get("PGNN_PRECISION", "tf32x3"), 1)
 
 
 def set_precision(name: str):
