@@ -30,7 +30,9 @@ constexpr int BM = 128;       // UMMA M (TMEM lanes)
 constexpr int BK = 16;        // fp32 elements of the reduction per stage = 2 UMMA k-steps of 8
 constexpr int NPRODUCER = 256;  // 8 producer warps (they also run the epilogue)
 constexpr int NTHREADS = NPRODUCER + 32;  // + one MMA-issuing warp
-constexpr int NSTAGE = 4;
+constexpr int NRAW = 6;   // ring of raw (= hi) operand stages filled by cp.async: deep, because L2 round trips are ~1-2 us under load
+constexpr int NLO = 2;    // ring of lo stages written by the producers just before a block is published
+constexpr int AHEAD = 4;  // cp.async groups in flight per thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -159,14 +161,23 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // Operand tile.  KC: source is contiguous along the reduction (element (r,k) at src[r*ld + k]); otherwise
 // contiguous along the row index (element (r,k) at src[k*ld + r]).  R = rows (MN extent) of the tile.
-// Each producer thread owns NV 16-byte pieces per block, the same ones in `issue` (cp.async raw -> smem)
-// and in `make_lo` (re-read own pieces, write x - trunc_tf32(x)).
+// Each producer thread owns NV 16-byte pieces per block, the same ones in `issue` (cp.async raw -> smem) and in
+// `make_lo` (re-read own pieces, write x - trunc_tf32(x)).  Everything that does not depend on the block index
+// (global pointer of the piece in block 0, smem offset, row validity) is computed ONCE in `init`: the main
+// loop is a pointer bump, one compare and the cp.async per piece — with only two producer warps per scheduler
+// the per-block address arithmetic (div/mod by non-powers of two, 64-bit multiplies) was what bounded it.
 template <bool KC, int R>
 struct Operand {
   static constexpr int VEC = R * BK / 4;
   static constexpr int NV = (VEC + NPRODUCER - 1) / NPRODUCER;
   // rounded to 1 KiB so that every buffer (the swizzled MN-major ones need 512 B atoms) starts aligned
   static constexpr int BYTES = ((KC ? kmajor_bytes(R) : mnmajor_bytes(R)) + 1023) / 1024 * 1024;
+
+  const float* gptr[NV];  // piece i of block 0
+  int soff[NV];           // byte offset inside an operand buffer; -1: this thread has no i-th piece
+  int kloc[NV];           // reduction index of the piece inside a block (K-major: first of 4; MN-major: the k row)
+  bool rok[NV];           // row index in range
+  int64_t step;           // pointer advance per block, in floats
 
   __device__ __forceinline__ static int smem_off(int f) {
     if (KC) {
@@ -176,41 +187,53 @@ struct Operand {
     const int k = f / (R / 4), rc = f % (R / 4);  // rc: group of 4 consecutive row indices
     return (rc >> 3) * MN_LBO + (k >> 2) * MN_SBO + (k & 3) * 128 + ((((rc >> 1) & 3) ^ (k & 3)) << 5) + (rc & 1) * 16;
   }
-  __device__ __forceinline__ static void issue(const float* __restrict__ src, int64_t ld, int r0, int rows, int k0, int kend,
-                                               uint8_t* raw) {
-    const uint32_t base = smem_u32(raw);
+  __device__ __forceinline__ void init(const float* __restrict__ src, int64_t ld, int r0, int rows, int k0) {
+    step = KC ? (int64_t)BK : (int64_t)BK * ld;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int f = threadIdx.x + i * NPRODUCER;
+      soff[i] = -1;
+      gptr[i] = src;
+      kloc[i] = 0;
+      rok[i] = false;
       if (f < VEC) {
-        const float* g = src;
-        uint32_t bytes = 0;
+        soff[i] = smem_off(f);
         if (KC) {
           const int r = f / (BK / 4), kc = f % (BK / 4);
-          const int gr = r0 + r, gk = k0 + kc * 4;
-          if (gr < rows && gk < kend) { g = src + (int64_t)gr * ld + gk; bytes = 16; }   // kend % 4 == 0
+          kloc[i] = kc * 4;
+          rok[i] = (r0 + r) < rows;
+          gptr[i] = src + (int64_t)(rok[i] ? r0 + r : 0) * ld + k0 + kc * 4;
         } else {
           const int k = f / (R / 4), rc = f % (R / 4);
-          const int gk = k0 + k, gr = r0 + rc * 4;
-          if (gk < kend && gr < rows) { g = src + (int64_t)gk * ld + gr; bytes = 16; }   // rows % 4 == 0
+          kloc[i] = k;
+          rok[i] = (r0 + rc * 4) < rows;                       // rows % 4 == 0
+          gptr[i] = src + (int64_t)(k0 + k) * ld + (rok[i] ? r0 + rc * 4 : 0);
         }
-        cp_async16(base + smem_off(f), g, bytes);  // bytes == 0: the 16 B are zero-filled
       }
     }
   }
-  __device__ __forceinline__ static void make_lo(const uint8_t* raw, uint8_t* lo) {
+  // krem = reduction elements left from this block's start (kend - k0 - kb*BK); kend % 4 == 0 for K-major sources
+  __device__ __forceinline__ void issue(int kb, int krem, uint8_t* raw) const {
+    const uint32_t base = smem_u32(raw);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int f = threadIdx.x + i * NPRODUCER;
-      if (f < VEC) {
-        const int off = smem_off(f);
-        const float4 v = *reinterpret_cast<const float4*>(raw + off);
+      if (soff[i] >= 0) {
+        const bool ok = rok[i] && kloc[i] < krem;
+        cp_async16(base + soff[i], ok ? gptr[i] + kb * step : gptr[i], ok ? 16u : 0u);  // 0 bytes: nothing is read, the 16 B are zero-filled
+      }
+    }
+  }
+  __device__ __forceinline__ void make_lo(const uint8_t* raw, uint8_t* lo) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (soff[i] >= 0) {
+        const float4 v = *reinterpret_cast<const float4*>(raw + soff[i]);
         float4 l;
         l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
         l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
         l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
         l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        *reinterpret_cast<float4*>(lo + off) = l;
+        *reinterpret_cast<float4*>(lo + soff[i]) = l;
       }
     }
   }
@@ -229,7 +252,7 @@ template <int BN>
 __host__ __device__ constexpr int tmem_cols() { return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512; }
 
 template <bool A_KC, bool B_KC, int BN>
-__host__ __device__ constexpr int smem_bytes() { return NSTAGE * 2 * (Operand<A_KC, BM>::BYTES + Operand<B_KC, BN>::BYTES) + 1024; }
+__host__ __device__ constexpr int smem_bytes() { return (NRAW + NLO) * (Operand<A_KC, BM>::BYTES + Operand<B_KC, BN>::BYTES) + 1024; }
 
 // C[m, n] = sum_r A(m, r) * B(n, r) over r in [kbeg, kend) of this split.
 // Warp roles: warps 0..7 = producers (global -> registers -> hi/lo split -> smem stage, then the epilogue),
@@ -243,15 +266,16 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   using OpA = Operand<A_KC, BM>;
   using OpB = Operand<B_KC, BN>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+  __shared__ __align__(8) uint64_t full_bar[NLO], raw_empty[NRAW], lo_empty[NLO], acc_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[BN];  // this tile's bias slice (zero past N), loaded once at the prologue
 
   uint8_t* bufs = smem;
-  auto a_hi = [&](int s) { return bufs + s * 2 * (OpA::BYTES + OpB::BYTES); };
-  auto a_lo = [&](int s) { return a_hi(s) + OpA::BYTES; };
-  auto b_hi = [&](int s) { return a_hi(s) + 2 * OpA::BYTES; };
-  auto b_lo = [&](int s) { return b_hi(s) + OpB::BYTES; };
+  constexpr int STAGE_BYTES = OpA::BYTES + OpB::BYTES;
+  auto a_hi = [&](int kb) { return bufs + (kb % NRAW) * STAGE_BYTES; };              // raw fp32 = hi operand
+  auto b_hi = [&](int kb) { return a_hi(kb) + OpA::BYTES; };
+  auto a_lo = [&](int kb) { return bufs + (NRAW + kb % NLO) * STAGE_BYTES; };
+  auto b_lo = [&](int kb) { return a_lo(kb) + OpA::BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -269,10 +293,11 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 32) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NLO; ++s) {
       mbar_init(smem_u32(&full_bar[s]), NPRODUCER / 32);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&lo_empty[s]), 1);
     }
+    for (int s = 0; s < NRAW; ++s) mbar_init(smem_u32(&raw_empty[s]), 1);
     mbar_init(smem_u32(&acc_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -285,23 +310,28 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
 
   if (warp < NPRODUCER / 32) {
     // ---------------- producers ----------------
-    // block kb: wait for its stage, cp.async the raw pieces (they double as the hi operand); then finish block
-    // kb-AHEAD: its cp.async group has landed, derive lo from this thread's own pieces and publish the stage.
-    constexpr int AHEAD = 2;
-    auto publish = [&](int kb) {
-      const int s = kb % NSTAGE;
-      OpA::make_lo(a_hi(s), a_lo(s));
-      OpB::make_lo(b_hi(s), b_lo(s));
-      fence_async_smem();  // cp.async-written raw tiles + the lo stores -> visible to the tensor core (async proxy)
+    // block kb: wait for its raw stage, cp.async the raw pieces (they double as the hi operand); then finish block
+    // kb-AHEAD: its cp.async group has landed, derive lo from this thread's own pieces and publish it.
+    OpA pa;
+    OpB pb;
+    pa.init(A, lda, m0, M, kbeg);
+    pb.init(B, ldb, n0, N, kbeg);
+    auto publish = [&](int j) {
+      if (j >= NLO) mbar_wait(smem_u32(&lo_empty[j % NLO]), ((j / NLO) - 1) & 1);  // MMAs of block j-NLO have read the lo stage
+      pa.make_lo(a_hi(j), a_lo(j));
+      pb.make_lo(b_hi(j), b_lo(j));
+      // No proxy fence here: on the producer side it drains the thread's whole memory pipeline, i.e. the cp.async
+      // groups still in flight, and turns the main loop into one L2 round trip per block (measured).  The
+      // mbarrier arrive (release) / wait (acquire) pair orders these generic-proxy writes before the MMA
+      // warp's fence.proxy.async, which then orders them before its tcgen05.mma reads.
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[j % NLO]));
     };
 #pragma unroll 1
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % NSTAGE;
-      if (kb >= NSTAGE) mbar_wait(smem_u32(&empty_bar[s]), ((kb / NSTAGE) - 1) & 1);  // MMAs of block kb-NSTAGE are done
-      OpA::issue(A, lda, m0, M, kbeg + kb * BK, kend, a_hi(s));
-      OpB::issue(B, ldb, n0, N, kbeg + kb * BK, kend, b_hi(s));
+      if (kb >= NRAW) mbar_wait(smem_u32(&raw_empty[kb % NRAW]), ((kb / NRAW) - 1) & 1);  // MMAs of block kb-NRAW are done
+      pa.issue(kb, kend - kbeg - kb * BK, a_hi(kb));
+      pb.issue(kb, kend - kbeg - kb * BK, b_hi(kb));
       cp_async_commit();
       if (kb >= AHEAD) {
         cp_async_wait<AHEAD>();  // all but the newest AHEAD groups are complete -> block kb-AHEAD has landed
@@ -310,19 +340,19 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
       }
     }
     cp_async_wait<0>();
-    for (int kb = (nkb > AHEAD ? nkb - AHEAD : 0); kb < nkb; ++kb) publish(kb);
+    for (int j = (nkb > AHEAD ? nkb - AHEAD : 0); j < nkb; ++j) publish(j);
     if (warp == 0) TC_TRACE(3);  // last block published
   } else {
     // ---------------- MMA issuer ----------------
 #pragma unroll 1
     for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % NSTAGE;
-      mbar_wait(smem_u32(&full_bar[s]), (kb / NSTAGE) & 1);
+      mbar_wait(smem_u32(&full_bar[kb % NLO]), (kb / NLO) & 1);
+      fence_async_smem();  // generic-proxy writes observed through the barrier -> async proxy (tensor core reads)
       tc_fence_after();
       if (kb == 0) TC_TRACE(4);        // MMA warp: first stage ready
       if (kb == nkb - 1) TC_TRACE(5);  // MMA warp: last stage ready
       if (lane == 0) {
-        const uint32_t ah = smem_u32(a_hi(s)), al = smem_u32(a_lo(s)), bh = smem_u32(b_hi(s)), bl = smem_u32(b_lo(s));
+        const uint32_t ah = smem_u32(a_hi(kb)), al = smem_u32(a_lo(kb)), bh = smem_u32(b_hi(kb)), bl = smem_u32(b_lo(kb));
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
           const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
@@ -330,7 +360,8 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
           umma_tf32(tmem_acc + BN, OpA::desc(ah, j), OpB::desc(bl, j), idesc, 1u);
           umma_tf32(tmem_acc, OpA::desc(ah, j), OpB::desc(bh, j), idesc, first);
         }
-        umma_commit(smem_u32(&empty_bar[s]));           // stage s is free once these MMAs have read it
+        umma_commit(smem_u32(&lo_empty[kb % NLO]));     // both rings are released by the completion of these MMAs
+        umma_commit(smem_u32(&raw_empty[kb % NRAW]));
         if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));  // accumulators complete
       }
       __syncwarp();
