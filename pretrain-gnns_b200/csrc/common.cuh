@@ -32,6 +32,20 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
+// Optional column reductions fused into the tensor-core GEMM epilogue (the output tile is already staged in shared
+// memory there).  All outputs must be zeroed by the caller; every CTA adds its tile's contribution with atomics.
+struct PgnnGemmHooks {
+  float* colsum = nullptr;   // [N]     += sum over rows of the (final) output              -> bias gradients
+  double* stats = nullptr;   // [2][N]  += sum, sum of squares (fp64)                        -> BatchNorm batch statistics
+  const float* S = nullptr;  // [M][Q]  per-row weights: gT[q][n] += sum_m S[m][q] out[m][n] -> bond-table gradients
+  int Q = 0;
+  float* gT = nullptr;       // rows [0, q_split)
+  float* gT2 = nullptr;      // rows [q_split, Q)
+  int q_split = 0;
+  int64_t ldt = 0;
+  bool any() const { return colsum || stats || S; }
+};
+
 // B200: 148 SMs.  Grids for grid-stride kernels are sized as a multiple of this.
 constexpr int kNumSMs = 148;
 

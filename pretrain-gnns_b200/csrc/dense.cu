@@ -164,9 +164,9 @@ k_colsum(const float* __restrict__ gy, int64_t ld, int M, int N, int rows_per_sp
 
 // tensor-core path (dense_tc.cu); returns PGNN_EUNSUPPORTED when the shape is not covered
 int pgnn_tc_linear_fwd(const float*, int64_t, const float*, const float*, int64_t, int64_t, int64_t, int, float*, int64_t,
-                       cudaStream_t);
+                       cudaStream_t, const PgnnGemmHooks*);
 int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, int64_t, const float*, int64_t, float*, int64_t,
-                         cudaStream_t);
+                         cudaStream_t, const PgnnGemmHooks*);
 int pgnn_tc_linear_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
 
 extern "C" {
@@ -178,7 +178,7 @@ int pgnn_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bi
   PGNN_CHECK_ARG(x && w && y && ldx >= K && ldy >= N);
   cudaStream_t st = as_stream(stream);
   if (precision == 1) {
-    int rc = pgnn_tc_linear_fwd(x, ldx, w, bias, M, N, K, relu, y, ldy, st);
+    int rc = pgnn_tc_linear_fwd(x, ldx, w, bias, M, N, K, relu, y, ldy, st, nullptr);
     if (rc != PGNN_EUNSUPPORTED) return rc;
   }
   Epilogue ep{bias, relu, nullptr, 0, 0};
@@ -195,7 +195,7 @@ int pgnn_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t M, 
   PGNN_CHECK_ARG(gy && w && gx && ldgy >= N && ldgx >= K);
   cudaStream_t st = as_stream(stream);
   if (precision == 1) {
-    int rc = pgnn_tc_linear_bwd_x(gy, ldgy, w, M, N, K, relu_src, ldr, gx, ldgx, st);
+    int rc = pgnn_tc_linear_bwd_x(gy, ldgy, w, M, N, K, relu_src, ldr, gx, ldgx, st, nullptr);
     if (rc != PGNN_EUNSUPPORTED) return rc;
   }
   // out[m, k] = sum_n gy[m, n] * w[n, k]: "N" of the template is K here, reduction runs over N

@@ -150,6 +150,7 @@ struct TcEpilogue {
   const float* mask_src;  // [M,N] (ld = ldm): zero where mask_src <= 0
   int64_t ldm;
   int atomic;             // split-K: accumulate with atomics into a zeroed output
+  PgnnGemmHooks hooks;    // fused column reductions over the final output tile (not with split-K)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -416,6 +417,7 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
     const int total = rows_here * C4;
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     const bool mvec_ok = ep.mask_src && ((ep.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask_src) & 15) == 0);
+    const bool want_hooks = ep.hooks.colsum || ep.hooks.stats || ep.hooks.S;
     for (int base = threadIdx.x; base < total; base += NPRODUCER * UNR) {
       float4 o[UNR], mk[UNR];
       int gm[UNR], gn[UNR];
@@ -453,6 +455,8 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
           if (ep.relu) ov[q] = fmaxf(ov[q], 0.f);
           ov[q] = mv[q] > 0.f ? ov[q] : 0.f;
         }
+        if (want_hooks)  // keep the final values in the staging tile for the column reductions below
+          *reinterpret_cast<float4*>(stage + (gm[u] - m0) * SLD + (gn[u] - n0)) = make_float4(ov[0], ov[1], ov[2], ov[3]);
         float* dst = C + (int64_t)gm[u] * ldc + gn[u];
         if (gn[u] + 3 < N && vec_ok) {
           if (ep.atomic) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(ov[0], ov[1], ov[2], ov[3]));
@@ -464,6 +468,46 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
               if (ep.atomic) atomicAdd(dst + q, ov[q]); else dst[q] = ov[q];
             }
         }
+      }
+    }
+  }
+  // (3) fused column reductions over the final tile: thread c owns output column n0 + c (conflict-free smem
+  //     column walks), one atomic per (CTA, column[, q]).
+  if (ep.hooks.colsum || ep.hooks.stats || ep.hooks.S) {
+    float* sS = stage + BM * SLD;  // [128][Q] slice of the per-row weights, behind the staging tile
+    const int rows_here = min(BM, M - m0);
+    if (ep.hooks.S)
+      for (int i = threadIdx.x; i < rows_here * ep.hooks.Q; i += NPRODUCER) sS[i] = ep.hooks.S[(int64_t)m0 * ep.hooks.Q + i];
+    asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
+    const int c = threadIdx.x;
+    if (c < BN && n0 + c < N) {
+      const int Q = ep.hooks.Q;
+      float s1 = 0.f;
+      double d1 = 0.0, d2 = 0.0;
+      float tq[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) tq[q] = 0.f;
+      for (int r = 0; r < rows_here; ++r) {
+        const float v = stage[r * SLD + c];
+        s1 += v;
+        if (ep.hooks.stats) { d1 += (double)v; d2 += (double)v * (double)v; }
+        if (ep.hooks.S) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q < Q) tq[q] = fmaf(sS[r * Q + q], v, tq[q]);
+        }
+      }
+      if (ep.hooks.colsum) atomicAdd(&ep.hooks.colsum[n0 + c], s1);
+      if (ep.hooks.stats) {
+        atomicAdd(&ep.hooks.stats[n0 + c], d1);
+        atomicAdd(&ep.hooks.stats[(int64_t)N + n0 + c], d2);
+      }
+      if (ep.hooks.S) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (q < Q)
+            atomicAdd(q < ep.hooks.q_split ? &ep.hooks.gT[(int64_t)q * ep.hooks.ldt + n0 + c]
+                                           : &ep.hooks.gT2[(int64_t)(q - ep.hooks.q_split) * ep.hooks.ldt + n0 + c], tq[q]);
       }
     }
   }
@@ -515,13 +559,18 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, i
   return PGNN_OK;
 }
 
-// Tile width.  Every CTA re-reads its 128 x K slab of A and its BN x K slab of B from L2, so narrow tiles
-// multiply operand traffic (measured: the main loop runs at the ~3 TB/s the L2 delivers to 16-byte cp.async
-// requests, not at tensor speed).  Take the widest candidate whose padding waste stays under ~15%.
+// Tile width.  Measured (profiles/r01_gemm_phases.md): the main loop runs at the rate one SM can pull operands
+// (~26 GB/s per SM at DRAM latency, all producer designs alike), so per-CTA time ~ (128 + BN) bytes per block.
+//   * if some width covers the problem in ONE wave (<= 148 CTAs incl. splits), take the narrowest such width:
+//     least work per CTA, most SMs busy;
+//   * otherwise (many waves) operand re-reads dominate: take the widest width with <= 15% padding waste.
 inline int pick_bn(int M, int N, int splits) {
-  (void)M; (void)splits;
-  const int cand[4] = {224, 160, 128, 64};
-  for (int bn : cand) {
+  const int cand[4] = {64, 128, 160, 224};
+  const int64_t mt = ceil_div(M, BM) * (splits > 0 ? splits : 1);
+  for (int bn : cand)
+    if (mt * ceil_div(N, bn) <= kNumSMs) return bn;
+  for (int i = 3; i >= 0; --i) {
+    const int bn = cand[i];
     const int padded = (int)ceil_div(N, bn) * bn;
     if (padded <= N + N * 15 / 100 || bn == 64) return bn;
   }
@@ -549,7 +598,7 @@ extern "C" __attribute__((visibility("default"))) int pgnn_debug_tc_trace(unsign
 extern "C" __attribute__((visibility("default"))) int pgnn_debug_tc_gemm(int a_kc, int b_kc, int bn, const float* A, int64_t lda,
                                                                         const float* B, int64_t ldb, float* C, int64_t ldc, int M,
                                                                         int N, int K, void* stream) {
-  TcEpilogue ep{nullptr, 0, nullptr, 0, 0};
+  TcEpilogue ep{nullptr, 0, nullptr, 0, 0, PgnnGemmHooks{}};
   cudaStream_t st = as_stream(stream);
   if (a_kc && b_kc) return dispatch<true, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
   if (a_kc && !b_kc) return dispatch<true, false>(bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
@@ -559,17 +608,17 @@ extern "C" __attribute__((visibility("default"))) int pgnn_debug_tc_gemm(int a_k
 
 // y[M,N] = act(x[M,K] . w[N,K]^T + bias)
 int pgnn_tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, int64_t M, int64_t N, int64_t K, int relu,
-                       float* y, int64_t ldy, cudaStream_t st) {
+                       float* y, int64_t ldy, cudaStream_t st, const PgnnGemmHooks* hooks) {
   if (K % 4 || ldx % 4 || !aligned16(x) || !aligned16(w) || !aligned16(y) || M < 1) return PGNN_EUNSUPPORTED;
-  TcEpilogue ep{bias, relu, nullptr, 0, 0};
+  TcEpilogue ep{bias, relu, nullptr, 0, 0, hooks ? *hooks : PgnnGemmHooks{}};
   return dispatch<true, true>(pick_bn((int)M, (int)N, 1), x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, 1, (int)K, ep, st);
 }
 
 // gx[M,K] = (gy[M,N] . w[N,K]) masked by relu_src > 0
 int pgnn_tc_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t M, int64_t N, int64_t K, const float* relu_src,
-                         int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st) {
+                         int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks) {
   if (N % 4 || K % 4 || ldgy % 4 || !aligned16(gy) || !aligned16(w) || !aligned16(gx) || M < 1) return PGNN_EUNSUPPORTED;
-  TcEpilogue ep{nullptr, 0, relu_src, ldr, 0};
+  TcEpilogue ep{nullptr, 0, relu_src, ldr, 0, hooks ? *hooks : PgnnGemmHooks{}};
   // output columns are K; the reduction runs over N; B(n_out = k, r = n) = w[r*K + k] is row-index contiguous
   return dispatch<true, false>(pick_bn((int)M, (int)K, 1), gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, 1, (int)N, ep, st);
 }
@@ -579,9 +628,13 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
                          float* gb, cudaStream_t st) {
   if (N % 4 || K % 4 || ldgy % 4 || ldx % 4 || !aligned16(gy) || !aligned16(x) || !aligned16(gw) || M < 1) return PGNN_EUNSUPPORTED;
   // output [N, K] (rows N = "M" of the MMA), reduction over the M node rows, split so the grid fills the chip
-  const int bn = pick_bn((int)N, (int)K, 1);
+  int bn = 224;  // the reduction is long and both operands are re-read per tile: widest tile with <= 15% padding
+  for (int c : {224, 160, 128, 64}) {
+    bn = c;
+    if ((int)ceil_div(K, c) * c <= K + K * 15 / 100) break;
+  }
   const int tiles = (int)(ceil_div(N, BM) * ceil_div(K, bn));
-  int splits = (int)ceil_div(kNumSMs, tiles);
+  int splits = kNumSMs / tiles;  // floor: 150 CTAs on 148 SMs would run as two waves
   // the tensor core accumulates with truncation: keep each TMEM chain <= 1024 rows, fold the rest in fp32 atomics
   if (splits < (int)ceil_div(M, 1024)) splits = (int)ceil_div(M, 1024);
   const int max_splits = (int)ceil_div(M, 2 * BK);
@@ -590,7 +643,7 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
   int per = (int)align_up(ceil_div(M, splits), BK);
   splits = (int)ceil_div(M, per);
   if (splits > 1) PGNN_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * N * K, st));
-  TcEpilogue ep{nullptr, 0, nullptr, 0, splits > 1};
+  TcEpilogue ep{nullptr, 0, nullptr, 0, splits > 1, PgnnGemmHooks{}};
   int rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
   if (rc != PGNN_OK) return rc;
   if (gb) {

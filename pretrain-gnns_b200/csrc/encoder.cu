@@ -17,6 +17,19 @@ int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_sca
                                 const float* S, int64_t Q, const float* T, const float* T2, int q_split, int64_t edge_off, float* out,
                                 int64_t ldo, cudaStream_t st);
 
+int pgnn_tc_linear_fwd(const float*, int64_t, const float*, const float*, int64_t, int64_t, int64_t, int, float*, int64_t,
+                       cudaStream_t, const PgnnGemmHooks*);
+int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, int64_t, const float*, int64_t, float*, int64_t,
+                         cudaStream_t, const PgnnGemmHooks*);
+int pgnn_tc_linear_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
+int pgnn_internal_bn_fwd_from_stats(const double* acc, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
+                                    float eps, int relu, float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale,
+                                    float* shift, cudaStream_t st);
+int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                                const float* beta, const float* save_mean, const float* save_invstd, int relu, float* gx,
+                                int64_t ldgx, float* ggamma, float* gbeta, float* colsum, void* workspace, cudaStream_t st);
+
 namespace {
 
 // order of the parameter pointer table and of the flat gradient layout
@@ -136,8 +149,29 @@ int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mea
     TRY(pgnn_internal_aggregate_fwd(h, D, in_scale, in_shift, in_scale != nullptr, N, D, w.rowptr_t, w.nbr_t, PGNN_AGG_SUM, nullptr, w.S, 9,
                                     (const float*)p[L_ET1], (const float*)p[L_ET2], 6, 0, aggr, D, as_stream(stream)));
     TRY(pgnn_linear_fwd(aggr, D, (const float*)p[L_W1], (const float*)p[L_B1], N, 2 * D, D, 1, z1, 2 * D, precision, stream));
-    TRY(pgnn_linear_fwd(z1, 2 * D, (const float*)p[L_W2], (const float*)p[L_B2], N, D, 2 * D, 0, z2, D, precision, stream));
-    if (training) {
+    // GEMM2; on the tensor path its epilogue also accumulates the BatchNorm batch statistics of z2 (fp64 atomics)
+    bool stats_fused = false;
+    if (training && precision == 1) {
+      double* acc = reinterpret_cast<double*>(w.scratch);
+      PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * D, as_stream(stream)));
+      PgnnGemmHooks hk;
+      hk.stats = acc;
+      const int rc = pgnn_tc_linear_fwd(z1, 2 * D, (const float*)p[L_W2], (const float*)p[L_B2], N, D, 2 * D, 0, z2, D, as_stream(stream), &hk);
+      if (rc == PGNN_OK) stats_fused = true;
+      else if (rc != PGNN_EUNSUPPORTED) return rc;
+    }
+    if (!stats_fused)
+      TRY(pgnn_linear_fwd(z1, 2 * D, (const float*)p[L_W2], (const float*)p[L_B2], N, D, 2 * D, 0, z2, D, precision, stream));
+    if (training && stats_fused) {
+      TRY(pgnn_internal_bn_fwd_from_stats(reinterpret_cast<double*>(w.scratch), z2, D, N, D, (const float*)p[L_GAMMA],
+                                          (const float*)p[L_BETA], (float*)bn_running_mean[l], (float*)bn_running_var[l],
+                                          bn_num_batches_tracked ? (int64_t*)bn_num_batches_tracked[l] : nullptr, momentum, eps, 0,
+                                          last ? node_rep : nullptr, ld_out, w.mean + l * D, w.invstd + l * D, w.scale + l * D,
+                                          w.shift + l * D, as_stream(stream)));
+      h = z2;
+      in_scale = w.scale + l * D;
+      in_shift = w.shift + l * D;
+    } else if (training) {
       // statistics only for inner layers (applied on load by the next gather); the last layer materialises node_rep
       TRY(pgnn_bn_fwd_train(z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], (float*)bn_running_mean[l],
                             (float*)bn_running_var[l], bn_num_batches_tracked ? (int64_t*)bn_num_batches_tracked[l] : nullptr, momentum,
@@ -182,17 +216,42 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
     const float* z1 = w.z1 + l * N * 2 * D;
     const float* z2 = w.z2 + l * N * D;
     const bool last = (l == L - 1);
-    // BatchNorm (+ReLU mask recomputed from z2) backward
-    TRY(pgnn_bn_bwd(gy, ldgy, z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], w.mean + l * D, w.invstd + l * D, !last,
-                    w.gz2, D, grads + o[L_GAMMA], grads + o[L_BETA], w.scratch, w.scratch_bytes, stream));
-    // MLP backward
-    TRY(pgnn_linear_bwd_w(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], grads + o[L_B2], precision, stream));
-    TRY(pgnn_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, precision, stream));
-    TRY(pgnn_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], grads + o[L_B1], precision, stream));
-    TRY(pgnn_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, precision, stream));
-    // bond tables: gT = S^T gaggr, rows 0..5 -> edge_embedding1, 6..8 -> edge_embedding2
-    PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));  // the two tables are adjacent in the layout
-    TRY(pgnn_internal_edge_table_bwd2(w.S, 9, w.gaggr, D, 0, N, (int)D, grads + o[L_ET1], D, grads + o[L_ET2], 6, st));
+    // BatchNorm (+ReLU mask recomputed from z2) backward; the same pass leaves colsum(gz2) = gradient of mlp.2.bias
+    TRY(pgnn_internal_bn_bwd_colsum(gy, ldgy, z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], w.mean + l * D,
+                                    w.invstd + l * D, !last, w.gz2, D, grads + o[L_GAMMA], grads + o[L_BETA], grads + o[L_B2],
+                                    w.scratch, st));
+    // MLP backward.  On the tensor path the dgrad epilogues carry the column reductions that would otherwise be
+    // passes of their own: colsum(gz1) = gradient of mlp.0.bias, and S^T gaggr = gradient of the two bond tables.
+    bool fused = false;
+    if (precision == 1) {
+      int rc = pgnn_tc_linear_bwd_w(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, st);
+      if (rc == PGNN_OK) {
+        PGNN_CUDA(cudaMemsetAsync(grads + o[L_B1], 0, sizeof(float) * 2 * D, st));
+        PgnnGemmHooks h1;
+        h1.colsum = grads + o[L_B1];
+        rc = pgnn_tc_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1);
+        if (rc != PGNN_OK) return rc;
+        rc = pgnn_tc_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], nullptr, st);
+        if (rc != PGNN_OK) return rc;
+        PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));  // the two tables are adjacent in the layout
+        PgnnGemmHooks h2;
+        h2.S = w.S; h2.Q = 9; h2.gT = grads + o[L_ET1]; h2.gT2 = grads + o[L_ET2]; h2.q_split = 6; h2.ldt = D;
+        rc = pgnn_tc_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2);
+        if (rc != PGNN_OK) return rc;
+        fused = true;
+      } else if (rc != PGNN_EUNSUPPORTED) {
+        return rc;
+      }
+    }
+    if (!fused) {
+      TRY(pgnn_linear_bwd_w(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, precision, stream));
+      TRY(pgnn_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, precision, stream));
+      TRY(pgnn_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], grads + o[L_B1], precision, stream));
+      TRY(pgnn_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, precision, stream));
+      // bond tables: gT = S^T gaggr, rows 0..5 -> edge_embedding1, 6..8 -> edge_embedding2
+      PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));
+      TRY(pgnn_internal_edge_table_bwd2(w.S, 9, w.gaggr, D, 0, N, (int)D, grads + o[L_ET1], D, grads + o[L_ET2], 6, st));
+    }
     // transpose-graph gather: gradient w.r.t. this layer's input rows
     TRY(pgnn_aggregate_bwd(w.gaggr, D, N, D, w.rowptr_s, w.nbr_s, PGNN_AGG_SUM, nullptr, w.rowptr_t, w.gh, D, stream));
     gy = w.gh;

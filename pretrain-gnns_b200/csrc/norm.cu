@@ -147,6 +147,40 @@ k_bn_bwd_apply(const float* __restrict__ gy, int64_t ldgy, const float* __restri
   }
 }
 
+// same arithmetic as k_bn_bwd_apply in the 32-column x 8-row-lane block shape of the statistics sweeps, so that the
+// column sums of gx (= the bias gradient of the Linear that produced x, chem/model.py:29 mlp[2]) fall out of the same pass
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply_colsum(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                      const float* __restrict__ invstd, int relu, const float* __restrict__ c1, const float* __restrict__ c2,
+                      float* __restrict__ gx, int64_t ldgx, float* __restrict__ colsum) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * kStatRows, r1 = min(M, r0 + kStatRows);
+  float acc = 0.f;
+  if (c < C) {
+    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c], k1 = c1[c], k2 = c2[c];
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float xhat = (x[(int64_t)r * ldx + c] - mu) * is;
+      float d = gy[(int64_t)r * ldgy + c];
+      if (relu && !(fmaf(xhat, ga, be) > 0.f)) d = 0.f;
+      const float v = ga * is * (d - k1 - xhat * k2);
+      gx[(int64_t)r * ldgx + c] = v;
+      acc += v;
+    }
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    atomicAdd(&colsum[c], t);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_relu_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy) {
   const int64_t total = M * C;
@@ -207,6 +241,42 @@ inline int grid_items(int64_t items, int threads) {
 }
 
 }  // namespace
+
+// encoder.cu: BatchNorm forward when the column sums / sums of squares were already accumulated (fp64, [2][C]) by the
+// epilogue of the GEMM that produced x (PgnnGemmHooks::stats)
+int pgnn_internal_bn_fwd_from_stats(const double* acc, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
+                                    float eps, int relu, float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale,
+                                    float* shift, cudaStream_t st) {
+  k_bn_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, gamma, beta, running_mean, running_var, nbt,
+                                                           momentum, eps, save_mean, save_invstd, scale, shift);
+  PGNN_LAUNCH_CHECK();
+  if (y) {
+    k_bn_apply<<<grid_items(M * C, 256), 256, 0, st>>>(x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy);
+    PGNN_LAUNCH_CHECK();
+  }
+  return PGNN_OK;
+}
+
+// encoder.cu: pgnn_bn_bwd that also leaves the column sums of gx in colsum[C] (OVERWRITTEN)
+int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
+                                const float* beta, const float* save_mean, const float* save_invstd, int relu, float* gx,
+                                int64_t ldgx, float* ggamma, float* gbeta, float* colsum, void* workspace, cudaStream_t st) {
+  double* acc = reinterpret_cast<double*>(workspace);
+  float* c1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(2 * C * 8, 256));
+  float* c2 = c1 + C;
+  PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
+  PGNN_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, st));
+  dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
+  k_bn_bwd_stats<<<g1, 256, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc);
+  PGNN_LAUNCH_CHECK();
+  k_bn_bwd_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, ggamma, gbeta, c1, c2);
+  PGNN_LAUNCH_CHECK();
+  k_bn_bwd_apply_colsum<<<g1, 256, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, c1, c2, gx,
+                                            ldgx, colsum);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
 
 extern "C" {
 
