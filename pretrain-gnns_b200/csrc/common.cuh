@@ -46,6 +46,16 @@ struct PgnnGemmHooks {
   bool any() const { return colsum || stats || S; }
 };
 
+// Epilogue of the tensor-core GEMM kernels (dense_tc.cu, dense_tma.cu)
+struct TcEpilogue {
+  const float* bias;      // [N] or null
+  int relu;
+  const float* mask_src;  // [M,N] (ld = ldm): zero where mask_src <= 0
+  int64_t ldm;
+  int atomic;             // split-K: accumulate with atomics into a zeroed output
+  PgnnGemmHooks hooks;    // fused column reductions over the final output tile (not with split-K)
+};
+
 // B200: 148 SMs.  Grids for grid-stride kernels are sized as a multiple of this.
 constexpr int kNumSMs = 148;
 

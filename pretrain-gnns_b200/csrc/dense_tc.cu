@@ -22,19 +22,21 @@
 //   * epilogue (producer warps): tcgen05.ld both accumulators -> add -> bias / ReLU / mask -> global.
 // No block-wide barrier and no register-staged global load sits in the main loop: the only waits are
 // the two mbarrier rings and the thread's own cp.async group.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "tc_common.cuh"
 
 namespace {
 
-constexpr int BM = 128;       // UMMA M (TMEM lanes)
 constexpr int BK = 16;        // fp32 elements of the reduction per stage = 2 UMMA k-steps of 8
-constexpr int NPRODUCER = 256;  // 8 producer warps (they also run the epilogue)
 constexpr int NTHREADS = NPRODUCER + 32;  // + one MMA-issuing warp
-constexpr int NRAW = 6;   // ring of raw (= hi) operand stages filled by cp.async: deep, because L2 round trips are ~1-2 us under load
-constexpr int NLO = 2;    // ring of lo stages written by the producers just before a block is published
-constexpr int AHEAD = 4;  // cp.async groups in flight per thread
+// Rings: raw (= hi) operand stages filled by cp.async, and lo stages written by the producers just before a block
+// is published.  Measured: deeper raw rings / more groups in flight do not raise the block rate (one SM pulls
+// ~26 GB/s through LDGSTS whatever the depth) but lengthen the pipeline fill, so the rings stay balanced.
+constexpr int NRAW = 4;
+constexpr int NLO = 4;
+constexpr int AHEAD = 2;  // cp.async groups in flight per thread
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // byte sizes of one operand buffer (hi or lo) for a tile of R rows (MN extent) x BK
 __host__ __device__ constexpr int kmajor_lbo(int R) { return R * 16 + 32; }          // stride between 16-byte k-chunks (+32: a quarter-warp = 2 rows x 4 chunks hits 8 distinct bank groups)
@@ -46,112 +48,6 @@ constexpr int MN_SBO = 512;
 constexpr int MN_LBO = (BK / 4) * MN_SBO;  // 2 KiB at BK = 16
 __host__ __device__ constexpr int mnmajor_bytes(int R) { return (R / 32) * MN_LBO; }
 
-// UMMA shared-memory matrix descriptor, version 1 (sm_100).
-// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version | [61,64) layout type
-// (0 = no swizzle, 1 = 128B swizzle with 32B base)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);
-}
-
-// instruction descriptor for kind::tf32, fp32 accumulate
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Time-bounded wait: a lost arrival traps after ~2 s (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const uint64_t t0 = globaltimer_ns();
-#pragma unroll 1
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((it & 1023u) == 1023u && globaltimer_ns() - t0 > 2000000000ull) break;
-  }
-  asm volatile("trap;");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-// hi = tf32(x) rounded to nearest; lo = x - hi is exact in fp32 (|lo| <= 2^-11 |x|) and is left unrounded: the
-// tensor core reads only its top 19 bits, an error of 2^-10 |lo| <= 2^-21 |x|, the same order as the dropped lo*lo.
-__device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
-#ifdef PGNN_TRUNC_SPLIT
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-#else
-  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-#endif
-  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-}
-
-// development trace: globaltimer stamps of CTA (0,0,0) at the phase boundaries (pgnn_debug_tc_trace reads it)
-__device__ unsigned long long g_tc_trace[16];
-#define TC_TRACE(slot)                                                                        \
-  do {                                                                                        \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) g_tc_trace[slot] = globaltimer_ns(); \
-  } while (0)
-
-struct TcEpilogue {
-  const float* bias;      // [N] or null
-  int relu;
-  const float* mask_src;  // [M,N] (ld = ldm): zero where mask_src <= 0
-  int64_t ldm;
-  int atomic;             // split-K: accumulate with atomics into a zeroed output
-  PgnnGemmHooks hooks;    // fused column reductions over the final output tile (not with split-K)
-};
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -244,13 +140,6 @@ struct Operand {
     return umma_desc(base + j * 2 * MN_SBO, MN_LBO, MN_SBO, 1);  // k-step = 8 k = two 4-deep atoms
   }
 };
-
-// Two fp32 accumulators per tile: hi*hi in columns [0,BN), the two cross terms in [BN,2BN).  The tensor
-// core adds each k-step into the accumulator with truncation, so the error of a chain grows with its
-// length; keeping the (2^-11 times smaller) cross terms out of the main chain cuts its length by 3x and
-// brings the GEMM to plain-fp32 accuracy (measured, tools/check_tc.py).
-template <int BN>
-__host__ __device__ constexpr int tmem_cols() { return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512; }
 
 template <bool A_KC, bool B_KC, int BN>
 __host__ __device__ constexpr int smem_bytes() { return (NRAW + NLO) * (Operand<A_KC, BM>::BYTES + Operand<B_KC, BN>::BYTES) + 1024; }
@@ -378,139 +267,7 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   tc_fence_after();
   if (warp == 0) TC_TRACE(6);  // accumulators complete, epilogue starts
 
-  // ---- epilogue ----
-  // (1) TMEM -> registers -> smem staging tile [128][BN+4] (the operand stages are free: every MMA has
-  //     completed).  Warp w owns TMEM lanes 32*(w%4).., column half w/4; both accumulators are summed here.
-  // (2) the 8 warps write the tile out row-contiguously (a warp instruction covers 512 consecutive bytes of
-  //     one output row), applying bias / ReLU / mask on the way.  Writing straight from the TMEM register
-  //     layout (one row per lane) would issue 16-byte stores to 32 different rows per instruction.
-  constexpr int SLD = BN + 4;  // staging row stride in floats: 16 B aligned, quarter-warps hit distinct banks
-  float* stage = reinterpret_cast<float*>(smem);
-  {
-    const int row = (warp & 3) * 32 + lane;
-    const int cbeg = (warp >> 2) * (BN / 2);
-#pragma unroll 1
-    for (int c = 0; c < BN / 2; c += 16) {
-      float v[16];
-      if (nkb > 0) {
-        float x[16];
-        tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cbeg + c), v);
-        tmem_ld16(tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN + cbeg + c), x);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += x[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      float* dst = stage + row * SLD + cbeg + c;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
-  }
-  if (warp == 0) TC_TRACE(9);
-  // only the producer warps take part from here on (the MMA warp has left through its own barrier below)
-  asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
-  {
-    constexpr int C4 = BN / 4;
-    constexpr int UNR = 4;  // independent row pieces per thread and trip: keeps the mask loads in flight together
-    const int rows_here = min(BM, M - m0);
-    const int total = rows_here * C4;
-    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    const bool mvec_ok = ep.mask_src && ((ep.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask_src) & 15) == 0);
-    const bool want_hooks = ep.hooks.colsum || ep.hooks.stats || ep.hooks.S;
-    for (int base = threadIdx.x; base < total; base += NPRODUCER * UNR) {
-      float4 o[UNR], mk[UNR];
-      int gm[UNR], gn[UNR];
-      bool live[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const int idx = base + u * NPRODUCER;
-        const int r = idx / C4, c4 = idx - r * C4;
-        gm[u] = m0 + r;
-        gn[u] = n0 + c4 * 4;
-        live[u] = idx < total && gn[u] < N;
-        mk[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (live[u]) {
-          o[u] = *reinterpret_cast<const float4*>(stage + r * SLD + c4 * 4);
-          if (ep.mask_src) {
-            const float* mp = ep.mask_src + (int64_t)gm[u] * ep.ldm + gn[u];
-            if (mvec_ok && gn[u] + 3 < N) mk[u] = *reinterpret_cast<const float4*>(mp);
-            else {
-              mk[u].x = mp[0];
-              mk[u].y = gn[u] + 1 < N ? mp[1] : 1.f;
-              mk[u].z = gn[u] + 2 < N ? mp[2] : 1.f;
-              mk[u].w = gn[u] + 3 < N ? mp[3] : 1.f;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (!live[u]) continue;
-        float ov[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
-        const float mv[4] = {mk[u].x, mk[u].y, mk[u].z, mk[u].w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (s_bias_on) ov[q] += s_bias[gn[u] - n0 + q];
-          if (ep.relu) ov[q] = fmaxf(ov[q], 0.f);
-          ov[q] = mv[q] > 0.f ? ov[q] : 0.f;
-        }
-        if (want_hooks)  // keep the final values in the staging tile for the column reductions below
-          *reinterpret_cast<float4*>(stage + (gm[u] - m0) * SLD + (gn[u] - n0)) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        float* dst = C + (int64_t)gm[u] * ldc + gn[u];
-        if (gn[u] + 3 < N && vec_ok) {
-          if (ep.atomic) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(ov[0], ov[1], ov[2], ov[3]));
-          else *reinterpret_cast<float4*>(dst) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (gn[u] + q < N) {
-              if (ep.atomic) atomicAdd(dst + q, ov[q]); else dst[q] = ov[q];
-            }
-        }
-      }
-    }
-  }
-  // (3) fused column reductions over the final tile: thread c owns output column n0 + c (conflict-free smem
-  //     column walks), one atomic per (CTA, column[, q]).
-  if (ep.hooks.colsum || ep.hooks.stats || ep.hooks.S) {
-    float* sS = stage + BM * SLD;  // [128][Q] slice of the per-row weights, behind the staging tile
-    const int rows_here = min(BM, M - m0);
-    if (ep.hooks.S)
-      for (int i = threadIdx.x; i < rows_here * ep.hooks.Q; i += NPRODUCER) sS[i] = ep.hooks.S[(int64_t)m0 * ep.hooks.Q + i];
-    asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
-    const int c = threadIdx.x;
-    if (c < BN && n0 + c < N) {
-      const int Q = ep.hooks.Q;
-      float s1 = 0.f;
-      double d1 = 0.0, d2 = 0.0;
-      float tq[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) tq[q] = 0.f;
-      for (int r = 0; r < rows_here; ++r) {
-        const float v = stage[r * SLD + c];
-        s1 += v;
-        if (ep.hooks.stats) { d1 += (double)v; d2 += (double)v * (double)v; }
-        if (ep.hooks.S) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q)
-            if (q < Q) tq[q] = fmaf(sS[r * Q + q], v, tq[q]);
-        }
-      }
-      if (ep.hooks.colsum) atomicAdd(&ep.hooks.colsum[n0 + c], s1);
-      if (ep.hooks.stats) {
-        atomicAdd(&ep.hooks.stats[n0 + c], d1);
-        atomicAdd(&ep.hooks.stats[(int64_t)N + n0 + c], d2);
-      }
-      if (ep.hooks.S) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          if (q < Q)
-            atomicAdd(q < ep.hooks.q_split ? &ep.hooks.gT[(int64_t)q * ep.hooks.ldt + n0 + c]
-                                           : &ep.hooks.gT2[(int64_t)(q - ep.hooks.q_split) * ep.hooks.ldt + n0 + c], tq[q]);
-      }
-    }
-  }
+  tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C, ldc, ep);
   if (warp == 0) TC_TRACE(7);  // warp 0 epilogue done
   tc_fence_before();
   __syncthreads();
@@ -590,6 +347,18 @@ int dispatch(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, f
 
 }  // namespace
 
+int pgnn_tma_gemm_kk(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                     const TcEpilogue& ep, cudaStream_t st);
+
+static bool tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_NO_TMA");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" __attribute__((visibility("default"))) int pgnn_debug_tc_trace(unsigned long long* host16) {
   return cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
 }
@@ -611,6 +380,10 @@ int pgnn_tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float*
                        float* y, int64_t ldy, cudaStream_t st, const PgnnGemmHooks* hooks) {
   if (K % 4 || ldx % 4 || !aligned16(x) || !aligned16(w) || !aligned16(y) || M < 1) return PGNN_EUNSUPPORTED;
   TcEpilogue ep{bias, relu, nullptr, 0, 0, hooks ? *hooks : PgnnGemmHooks{}};
+  if (tma_enabled()) {  // both operands reduction-contiguous: TMA-staged kernel (dense_tma.cu)
+    const int rc = pgnn_tma_gemm_kk(pick_bn((int)M, (int)N, 1), x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, ep, st);
+    if (rc != PGNN_EUNSUPPORTED) return rc;
+  }
   return dispatch<true, true>(pick_bn((int)M, (int)N, 1), x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, 1, (int)K, ep, st);
 }
 
@@ -621,6 +394,51 @@ int pgnn_tc_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t 
   TcEpilogue ep{nullptr, 0, relu_src, ldr, 0, hooks ? *hooks : PgnnGemmHooks{}};
   // output columns are K; the reduction runs over N; B(n_out = k, r = n) = w[r*K + k] is row-index contiguous
   return dispatch<true, false>(pick_bn((int)M, (int)K, 1), gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, 1, (int)N, ep, st);
+}
+
+// dgrad with the TRANSPOSED weight at hand: gx[M,K] = gy[M,N] . wT[K,N]^T — both operands reduction-contiguous, so the
+// TMA-staged kernel applies (encoder.cu transposes the 2L weight matrices once per backward)
+int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int64_t M, int64_t N, int64_t K, const float* relu_src,
+                            int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks) {
+  if (!tma_enabled() || N % 4 || ldgy % 4 || !aligned16(gy) || !aligned16(wT) || !aligned16(gx) || M < 1) return PGNN_EUNSUPPORTED;
+  TcEpilogue ep{nullptr, 0, relu_src, ldr, 0, hooks ? *hooks : PgnnGemmHooks{}};
+  return pgnn_tma_gemm_kk(pick_bn((int)M, (int)K, 1), gy, ldgy, wT, N, gx, ldgx, (int)M, (int)K, (int)N, ep, st);
+}
+
+// out[c][r] = in[r][c] for a batch of row-major matrices (weights: a few hundred KB each)
+namespace {
+struct TransposeJob { const float* in; float* out; int rows, cols; };
+constexpr int kMaxTransposeJobs = 32;
+struct TransposeBatch { TransposeJob job[kMaxTransposeJobs]; };
+__global__ void __launch_bounds__(256) k_transpose_batch(TransposeBatch b) {
+  __shared__ float tile[32][33];
+  const TransposeJob j = b.job[blockIdx.z];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= j.cols || r0 >= j.rows) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < j.rows && c0 + tx < j.cols) tile[i][tx] = j.in[(int64_t)(r0 + i) * j.cols + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < j.cols && r0 + tx < j.rows) j.out[(int64_t)(c0 + i) * j.rows + r0 + tx] = tile[tx][i];
+}
+}  // namespace
+
+int pgnn_internal_transpose_batch(int count, const float* const* in, float* const* out, const int* rows, const int* cols,
+                                  cudaStream_t st) {
+  if (count <= 0) return PGNN_OK;
+  if (count > kMaxTransposeJobs) return PGNN_EUNSUPPORTED;
+  TransposeBatch b;
+  int mr = 0, mc = 0;
+  for (int i = 0; i < count; ++i) {
+    b.job[i] = TransposeJob{in[i], out[i], rows[i], cols[i]};
+    mr = rows[i] > mr ? rows[i] : mr;
+    mc = cols[i] > mc ? cols[i] : mc;
+  }
+  dim3 grid((unsigned)ceil_div(mc, 32), (unsigned)ceil_div(mr, 32), (unsigned)count);
+  k_transpose_batch<<<grid, 256, 0, st>>>(b);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
 }
 
 // gw[N,K] = gy[M,N]^T . x[M,K]; gb[N] = column sums of gy

@@ -1,0 +1,226 @@
+// 3xTF32 GEMM with TMA-staged operands, for the case where BOTH operands are contiguous along the reduction
+// (forward Linear: y = x . w^T; dgrad when the transposed weight is available).
+//
+// dense_tc.cu feeds the tensor core with cp.async, which one SM can only drive at ~26 GB/s (LDGSTS issue rate /
+// requests in flight; profiles/r01_gemm_phases.md).  Here one thread issues two cp.async.bulk.tensor.2d per
+// 32-deep reduction block (A box 128 x 32 fp32, B box BN x 32 fp32, 128B-swizzled, zero-filled out of bounds)
+// and the copy engine completes them on an mbarrier:
+//
+//   warp 9   TMA producer: wait raw_empty[s] -> expect_tx -> 2 tensor copies into raw stage s
+//   warps 0-7 converters: wait raw_full[s] (+ lo_empty[t]) -> lo = x - trunc_tf32(x), a LINEAR pass over the stage
+//            (the swizzle is irrelevant for an element-wise map onto an identically laid out buffer) -> arrive lo_full[t]
+//   warp 8   MMA issuer: wait lo_full[t] -> fence.proxy.async -> 4 k-steps x 3 tcgen05.mma (raw tile = hi operand,
+//            SWIZZLE_128B K-major descriptors, start address advanced 32 B per k-step) -> commit lo_empty[t], raw_empty[s]
+//   epilogue (warps 0-7): tc_common.cuh, identical to dense_tc.cu (two accumulators, staged coalesced stores, hooks).
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TBK = 32;                         // fp32 per reduction block = one 128-byte swizzle row
+constexpr int T_NTHREADS = NPRODUCER + 64;      // 8 converter/epilogue warps + MMA warp + TMA warp
+constexpr int T_NLO = 2;
+
+template <int BN>
+struct TmaCfg {
+  static constexpr int A_BYTES = BM * TBK * 4;  // 16 KiB
+  static constexpr int B_BYTES = BN * TBK * 4;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NRAW = (STAGE <= 32768) ? 3 : 2;
+  static constexpr int SMEM = (NRAW + T_NLO) * STAGE + 1024;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+// K-major operand, SWIZZLE_128B (layout type 2): 8-row groups are 1024 B apart; LBO is unused for swizzled K-major
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(T_NTHREADS, 1)
+k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
+                  int64_t ldc, int M, int N, int K, TcEpilogue ep) {
+  using Cfg = TmaCfg<BN>;
+  constexpr int NRAW = Cfg::NRAW;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], lo_full[T_NLO], lo_empty[T_NLO], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[BN];
+
+  auto raw = [&](int kb) { return smem + (kb % NRAW) * Cfg::STAGE; };             // [A raw | B raw]
+  auto lo = [&](int kb) { return smem + (NRAW + kb % T_NLO) * Cfg::STAGE; };     // [A lo | B lo]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + TBK - 1) / TBK;
+  const bool s_bias_on = ep.bias != nullptr;
+  for (int i = threadIdx.x; i < BN; i += T_NTHREADS) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)tmem_cols<BN>())
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < NRAW; ++s) {
+      mbar_init(smem_u32(&raw_full[s]), 1);
+      mbar_init(smem_u32(&raw_empty[s]), 1);
+    }
+    for (int s = 0; s < T_NLO; ++s) {
+      mbar_init(smem_u32(&lo_full[s]), NPRODUCER / 32);
+      mbar_init(smem_u32(&lo_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&acc_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_s;
+  constexpr uint32_t idesc = umma_idesc(BM, BN, false, false);
+
+  if (warp == 9) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NRAW;
+        if (kb >= NRAW) mbar_wait(smem_u32(&raw_empty[s]), ((kb / NRAW) - 1) & 1);
+        mbar_expect_tx(smem_u32(&raw_full[s]), Cfg::STAGE);  // a box is always written in full (zero-filled out of bounds)
+        tma_load_2d(smem_u32(raw(kb)), &tmap_a, smem_u32(&raw_full[s]), kb * TBK, m0);
+        tma_load_2d(smem_u32(raw(kb)) + Cfg::A_BYTES, &tmap_b, smem_u32(&raw_full[s]), kb * TBK, n0);
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(smem_u32(&lo_full[kb % T_NLO]), (kb / T_NLO) & 1);
+      fence_async_smem();  // the converters' generic-proxy lo stores, observed through the barrier -> async proxy
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t ah = smem_u32(raw(kb)), bh = ah + Cfg::A_BYTES, al = smem_u32(lo(kb)), bl = al + Cfg::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < TBK / 8; ++j) {
+          const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
+          const uint32_t ko = j * 32;  // 8 fp32 = 32 B inside the 128 B swizzle row
+          umma_tf32(tmem_acc + BN, umma_desc_sw128(al + ko), umma_desc_sw128(bh + ko), idesc, first);  // cross terms
+          umma_tf32(tmem_acc + BN, umma_desc_sw128(ah + ko), umma_desc_sw128(bl + ko), idesc, 1u);
+          umma_tf32(tmem_acc, umma_desc_sw128(ah + ko), umma_desc_sw128(bh + ko), idesc, first);
+        }
+        umma_commit(smem_u32(&lo_empty[kb % T_NLO]));
+        umma_commit(smem_u32(&raw_empty[kb % NRAW]));
+        if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- converters ----------------
+    constexpr int V4 = Cfg::STAGE / 16;
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(smem_u32(&raw_full[kb % NRAW]), (kb / NRAW) & 1);  // TMA bytes have landed
+      if (kb >= T_NLO) mbar_wait(smem_u32(&lo_empty[kb % T_NLO]), ((kb / T_NLO) - 1) & 1);
+      const float4* src = reinterpret_cast<const float4*>(raw(kb));
+      float4* dst = reinterpret_cast<float4*>(lo(kb));
+#pragma unroll 4
+      for (int i = threadIdx.x; i < V4; i += NPRODUCER) {
+        const float4 v = src[i];
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        dst[i] = l;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&lo_full[kb % T_NLO]));
+    }
+  }
+  if (warp >= NPRODUCER / 32) {
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
+  if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
+  tc_fence_after();
+  tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C, ldc, ep);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major fp32 [rows, cols] with row stride ld (elements): box = [box_rows x 32 cols], 128B swizzle, zero OOB fill
+bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+               const TcEpilogue& ep, cudaStream_t st) {
+  alignas(64) CUtensorMap ma, mb;
+  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, BN)) return PGNN_EUNSUPPORTED;
+  constexpr int smem = TmaCfg<BN>::SMEM;
+  static bool configured = false;
+  if (!configured) {
+    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
+  k_gemm_3xtf32_tma<BN><<<grid, T_NTHREADS, smem, st>>>(ma, mb, C, ldc, M, N, K, ep);
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+}  // namespace
+
+// C[M,N] = A[M,K] . B[N,K]^T (+ epilogue); both operands reduction-contiguous.  PGNN_EUNSUPPORTED when the layout does
+// not meet the TMA constraints (16-byte aligned base, row stride multiple of 16 bytes) or the driver entry is missing.
+int pgnn_tma_gemm_kk(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                     const TcEpilogue& ep, cudaStream_t st) {
+  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return PGNN_EUNSUPPORTED;
+  switch (bn) {
+    case 64: return launch_tma<64>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
+    case 128: return launch_tma<128>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
+    case 160: return launch_tma<160>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
+    default: return launch_tma<224>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
+  }
+}

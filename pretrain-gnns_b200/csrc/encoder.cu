@@ -22,6 +22,10 @@ int pgnn_tc_linear_fwd(const float*, int64_t, const float*, const float*, int64_
 int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, int64_t, const float*, int64_t, float*, int64_t,
                          cudaStream_t, const PgnnGemmHooks*);
 int pgnn_tc_linear_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
+int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int64_t M, int64_t N, int64_t K, const float* relu_src,
+                            int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks);
+int pgnn_internal_transpose_batch(int count, const float* const* in, float* const* out, const int* rows, const int* cols,
+                                  cudaStream_t st);
 int pgnn_internal_bn_fwd_from_stats(const double* acc, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
                                     const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
                                     float eps, int relu, float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale,
@@ -53,6 +57,7 @@ struct Ws {
   float *S, *h0, *scale, *shift, *mean, *invstd;  // scale/shift/mean/invstd: [L, D]
   float *aggr, *z1, *z2;                           // [L, N, D], [L, N, 2D], [L, N, D]
   float *gh, *gz2, *gz1, *gaggr;                   // backward temporaries
+  float* wT;                                       // [L][2][2D*D]: mlp.0.weight^T, mlp.2.weight^T (dgrad B operands)
   void* scratch;                                   // bucket / BatchNorm scratch
   int64_t scratch_bytes, total;
 };
@@ -80,6 +85,7 @@ Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.gz2 = c.take<float>(N * D);
   w.gz1 = c.take<float>(N * 2 * D);
   w.gaggr = c.take<float>(N * D);
+  w.wT = c.take<float>(L * 4 * D * D);
   int64_t sb = pgnn_graph_prep_workspace_bytes(N, E);
   const int64_t bb = pgnn_bn_workspace_bytes(N > 0 ? N : 1, D);
   if (bb > sb) sb = bb;
@@ -207,6 +213,22 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
   }
   PGNN_CHECK_ARG(g_node_rep && x);
   Ws w = carve(workspace, N, E, L, D);
+  // transposed copies of the 2L MLP weights: with them every dgrad has both operands reduction-contiguous and runs on
+  // the TMA-staged GEMM (dense_tma.cu) instead of the cp.async one
+  bool have_wT = false;
+  if (precision == 1 && 2 * L <= 32) {
+    const float* in[32];
+    float* out[32];
+    int rows[32], cols[32];
+    for (int64_t l = 0; l < L; ++l) {
+      const void* const* p = params + P_LAYER0 + l * L_COUNT;
+      in[2 * l] = (const float*)p[L_W1];     out[2 * l] = w.wT + (2 * l) * 2 * D * D;     rows[2 * l] = (int)(2 * D); cols[2 * l] = (int)D;
+      in[2 * l + 1] = (const float*)p[L_W2]; out[2 * l + 1] = w.wT + (2 * l + 1) * 2 * D * D; rows[2 * l + 1] = (int)D; cols[2 * l + 1] = (int)(2 * D);
+    }
+    const int rc = pgnn_internal_transpose_batch((int)(2 * L), in, out, rows, cols, st);
+    if (rc == PGNN_OK) have_wT = true;
+    else if (rc != PGNN_EUNSUPPORTED) return rc;
+  }
   const float* gy = g_node_rep;
   int64_t ldgy = ldg;
   for (int64_t l = L - 1; l >= 0; --l) {
@@ -229,14 +251,20 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
         PGNN_CUDA(cudaMemsetAsync(grads + o[L_B1], 0, sizeof(float) * 2 * D, st));
         PgnnGemmHooks h1;
         h1.colsum = grads + o[L_B1];
-        rc = pgnn_tc_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1);
+        rc = have_wT ? pgnn_tc_linear_bwd_x_wt(w.gz2, D, w.wT + (2 * l + 1) * 2 * D * D, N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1)
+                     : PGNN_EUNSUPPORTED;
+        if (rc == PGNN_EUNSUPPORTED)
+          rc = pgnn_tc_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1);
         if (rc != PGNN_OK) return rc;
         rc = pgnn_tc_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], nullptr, st);
         if (rc != PGNN_OK) return rc;
         PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));  // the two tables are adjacent in the layout
         PgnnGemmHooks h2;
         h2.S = w.S; h2.Q = 9; h2.gT = grads + o[L_ET1]; h2.gT2 = grads + o[L_ET2]; h2.q_split = 6; h2.ldt = D;
-        rc = pgnn_tc_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2);
+        rc = have_wT ? pgnn_tc_linear_bwd_x_wt(w.gz1, 2 * D, w.wT + (2 * l) * 2 * D * D, N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2)
+                     : PGNN_EUNSUPPORTED;
+        if (rc == PGNN_EUNSUPPORTED)
+          rc = pgnn_tc_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2);
         if (rc != PGNN_OK) return rc;
         fused = true;
       } else if (rc != PGNN_EUNSUPPORTED) {

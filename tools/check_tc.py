@@ -60,6 +60,7 @@ def run(M, N, K, seed=0):
 
 
 if __name__ == "__main__":
+    print("PGNN_NO_TMA =", os.environ.get("PGNN_NO_TMA"))
     if len(sys.argv) > 1 and sys.argv[1] == "warm":
         COLD = False
         print("warm L2 (no flush between launches)")
