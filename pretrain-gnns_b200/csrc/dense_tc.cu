@@ -349,6 +349,8 @@ int dispatch(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, f
 
 int pgnn_tma_gemm_kk(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
                      const TcEpilogue& ep, cudaStream_t st);
+int pgnn_tma_gemm(bool a_mn, bool b_mn, int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+                  int N, int K, int splits, int k_per_split, const TcEpilogue& ep, cudaStream_t st);
 
 static bool tma_enabled() {
   static int v = -1;
@@ -392,6 +394,10 @@ int pgnn_tc_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t 
                          int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks) {
   if (N % 4 || K % 4 || ldgy % 4 || !aligned16(gy) || !aligned16(w) || !aligned16(gx) || M < 1) return PGNN_EUNSUPPORTED;
   TcEpilogue ep{nullptr, 0, relu_src, ldr, 0, hooks ? *hooks : PgnnGemmHooks{}};
+  if (tma_enabled()) {  // A reduction-contiguous, B = w row-index-contiguous (MN-major boxes)
+    const int rc = pgnn_tma_gemm(false, true, pick_bn((int)M, (int)K, 1), gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, 1, (int)N, ep, st);
+    if (rc != PGNN_EUNSUPPORTED) return rc;
+  }
   // output columns are K; the reduction runs over N; B(n_out = k, r = n) = w[r*K + k] is row-index contiguous
   return dispatch<true, false>(pick_bn((int)M, (int)K, 1), gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, 1, (int)N, ep, st);
 }
@@ -458,11 +464,13 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
   const int max_splits = (int)ceil_div(M, 2 * BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  int per = (int)align_up(ceil_div(M, splits), BK);
+  int per = (int)align_up(ceil_div(M, splits), 32);  // multiple of the TMA kernel's 32-deep block (and of BK)
   splits = (int)ceil_div(M, per);
   if (splits > 1) PGNN_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * N * K, st));
   TcEpilogue ep{nullptr, 0, nullptr, 0, splits > 1, PgnnGemmHooks{}};
-  int rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+  int rc = PGNN_EUNSUPPORTED;
+  if (tma_enabled()) rc = pgnn_tma_gemm(true, true, bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+  if (rc == PGNN_EUNSUPPORTED) rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
   if (rc != PGNN_OK) return rc;
   if (gb) {
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));

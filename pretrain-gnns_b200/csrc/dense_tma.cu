@@ -1,5 +1,7 @@
-// 3xTF32 GEMM with TMA-staged operands, for the case where BOTH operands are contiguous along the reduction
-// (forward Linear: y = x . w^T; dgrad when the transposed weight is available).
+// 3xTF32 GEMM with TMA-staged operands.  Operands may be reduction-contiguous ("K-major": element (r,k) at
+// src[r*ld + k]; one 128B-swizzled box [R x 32] per block) or row-index-contiguous ("MN-major": element (r,k) at
+// src[k*ld + r]; R/32 boxes [32 k x 32 r] in the 128B-swizzle / 32B-atom mode, the only layout tf32 accepts transposed).
+// fwd = K/K, dgrad = K/MN (or K/K with a transposed weight), wgrad = MN/MN with split-K.
 //
 // dense_tc.cu feeds the tensor core with cp.async, which one SM can only drive at ~26 GB/s (LDGSTS issue rate /
 // requests in flight; profiles/r01_gemm_phases.md).  Here one thread issues two cp.async.bulk.tensor.2d per
@@ -24,12 +26,13 @@ constexpr int T_NLO = 2;
 
 template <int BN>
 struct TmaCfg {
-  static constexpr int A_BYTES = BM * TBK * 4;  // 16 KiB
+  static constexpr int A_BYTES = BM * TBK * 4;  // 16 KiB (either major: R rows x 32 k x 4 B)
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NRAW = (STAGE <= 32768) ? 3 : 2;
   static constexpr int SMEM = (NRAW + T_NLO) * STAGE + 1024;
 };
+constexpr int MNB_BYTES = 32 * TBK * 4;  // one MN-major box: 32 k rows x 128 B
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -44,11 +47,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// descriptor of k-step j (8 reduction elements) of a staged operand
+template <bool MN>
+__device__ __forceinline__ uint64_t tma_desc(uint32_t base, int j) {
+  if (MN) return umma_desc(base + j * 1024, MNB_BYTES, 512, 1);  // 32-row blocks 4 KiB apart, 4-deep k groups 512 B apart
+  return umma_desc_sw128(base + j * 32);                         // 8 fp32 = 32 B inside the 128 B swizzle row
+}
 
-template <int BN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(T_NTHREADS, 1)
 k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
-                  int64_t ldc, int M, int N, int K, TcEpilogue ep) {
+                  int64_t ldc, int M, int N, int K, int k_per_split, TcEpilogue ep) {
   using Cfg = TmaCfg<BN>;
   constexpr int NRAW = Cfg::NRAW;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -61,8 +70,10 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + TBK - 1) / TBK;
-  const bool s_bias_on = ep.bias != nullptr;
+  const int kbeg = blockIdx.z * k_per_split;  // k_per_split % 32 == 0 whenever there is more than one split
+  const int kend = min(K, kbeg + k_per_split);
+  const int nkb = (kend - kbeg + TBK - 1) / TBK;
+  const bool s_bias_on = ep.bias != nullptr && blockIdx.z == 0;
   for (int i = threadIdx.x; i < BN; i += T_NTHREADS) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
 
   if (warp == 0) {
@@ -87,7 +98,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
-  constexpr uint32_t idesc = umma_idesc(BM, BN, false, false);
+  constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
 
   if (warp == 9) {
     // ---------------- TMA producer ----------------
@@ -99,8 +110,20 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int s = kb % NRAW;
         if (kb >= NRAW) mbar_wait(smem_u32(&raw_empty[s]), ((kb / NRAW) - 1) & 1);
         mbar_expect_tx(smem_u32(&raw_full[s]), Cfg::STAGE);  // a box is always written in full (zero-filled out of bounds)
-        tma_load_2d(smem_u32(raw(kb)), &tmap_a, smem_u32(&raw_full[s]), kb * TBK, m0);
-        tma_load_2d(smem_u32(raw(kb)) + Cfg::A_BYTES, &tmap_b, smem_u32(&raw_full[s]), kb * TBK, n0);
+        const int k0 = kbeg + kb * TBK;
+        const uint32_t bar = smem_u32(&raw_full[s]), da = smem_u32(raw(kb)), db = da + Cfg::A_BYTES;
+        if (A_MN) {
+#pragma unroll
+          for (int b = 0; b < BM / 32; ++b) tma_load_2d(da + b * MNB_BYTES, &tmap_a, bar, m0 + 32 * b, k0);
+        } else {
+          tma_load_2d(da, &tmap_a, bar, k0, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int b = 0; b < BN / 32; ++b) tma_load_2d(db + b * MNB_BYTES, &tmap_b, bar, n0 + 32 * b, k0);
+        } else {
+          tma_load_2d(db, &tmap_b, bar, k0, n0);
+        }
       }
     }
   } else if (warp == 8) {
@@ -115,10 +138,9 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < TBK / 8; ++j) {
           const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
-          const uint32_t ko = j * 32;  // 8 fp32 = 32 B inside the 128 B swizzle row
-          umma_tf32(tmem_acc + BN, umma_desc_sw128(al + ko), umma_desc_sw128(bh + ko), idesc, first);  // cross terms
-          umma_tf32(tmem_acc + BN, umma_desc_sw128(ah + ko), umma_desc_sw128(bl + ko), idesc, 1u);
-          umma_tf32(tmem_acc, umma_desc_sw128(ah + ko), umma_desc_sw128(bh + ko), idesc, first);
+          umma_tf32(tmem_acc + BN, tma_desc<A_MN>(al, j), tma_desc<B_MN>(bh, j), idesc, first);  // cross terms
+          umma_tf32(tmem_acc + BN, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bl, j), idesc, 1u);
+          umma_tf32(tmem_acc, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bh, j), idesc, first);
         }
         umma_commit(smem_u32(&lo_empty[kb % T_NLO]));
         umma_commit(smem_u32(&raw_empty[kb % NRAW]));
@@ -181,46 +203,65 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major fp32 [rows, cols] with row stride ld (elements): box = [box_rows x 32 cols], 128B swizzle, zero OOB fill
-bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// Tensor map of one operand of extent R (row index) x Kred (reduction):
+//   K-major  (element (r,k) at base[r*ld + k]): global tensor [R][Kred], box [box_r x 32 k], SWIZZLE_128B
+//   MN-major (element (r,k) at base[k*ld + r]): global tensor [Kred][R], box [32 k x 32 r], SWIZZLE_128B_ATOM_32B
+bool make_map(CUtensorMap* map, const float* base, bool mn, int64_t R, int64_t Kred, int64_t ld, int box_r) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)(mn ? R : Kred), (cuuint64_t)(mn ? Kred : R)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {32u, (cuuint32_t)(mn ? TBK : box_r)};
   cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
-int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
-               const TcEpilogue& ep, cudaStream_t st) {
+template <bool A_MN, bool B_MN, int BN>
+int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits,
+               int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
   alignas(64) CUtensorMap ma, mb;
-  if (!make_map(&ma, A, M, K, lda, BM) || !make_map(&mb, B, N, K, ldb, BN)) return PGNN_EUNSUPPORTED;
+  if (!make_map(&ma, A, A_MN, M, K, lda, BM) || !make_map(&mb, B, B_MN, N, K, ldb, BN)) return PGNN_EUNSUPPORTED;
   constexpr int smem = TmaCfg<BN>::SMEM;
   static bool configured = false;
   if (!configured) {
-    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
-  k_gemm_3xtf32_tma<BN><<<grid, T_NTHREADS, smem, st>>>(ma, mb, C, ldc, M, N, K, ep);
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
+  k_gemm_3xtf32_tma<A_MN, B_MN, BN><<<grid, T_NTHREADS, smem, st>>>(ma, mb, C, ldc, M, N, K, k_per_split, ep);
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
 
+template <bool A_MN, bool B_MN>
+int dispatch_tma(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                 int splits, int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_tma<A_MN, B_MN, 64>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+    case 128: return launch_tma<A_MN, B_MN, 128>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+    case 160: return launch_tma<A_MN, B_MN, 160>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+    default: return launch_tma<A_MN, B_MN, 224>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+  }
+}
+
 }  // namespace
 
-// C[M,N] = A[M,K] . B[N,K]^T (+ epilogue); both operands reduction-contiguous.  PGNN_EUNSUPPORTED when the layout does
+// C[M,N] = sum_k A(m,k) B(n,k) (+ epilogue) with TMA-staged operands; a_mn / b_mn select the operand major (see the top
+// of the file).  splits > 1 requires k_per_split % 32 == 0 and an atomic epilogue.  PGNN_EUNSUPPORTED when the layout does
 // not meet the TMA constraints (16-byte aligned base, row stride multiple of 16 bytes) or the driver entry is missing.
+int pgnn_tma_gemm(bool a_mn, bool b_mn, int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M,
+                  int N, int K, int splits, int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
+  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return PGNN_EUNSUPPORTED;
+  if (splits > 1 && (k_per_split % TBK)) return PGNN_EUNSUPPORTED;
+  if (!a_mn && !b_mn) return dispatch_tma<false, false>(bn, A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+  if (!a_mn && b_mn) return dispatch_tma<false, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+  if (a_mn && b_mn) return dispatch_tma<true, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+  return PGNN_EUNSUPPORTED;
+}
+
 int pgnn_tma_gemm_kk(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
                      const TcEpilogue& ep, cudaStream_t st) {
-  if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return PGNN_EUNSUPPORTED;
-  switch (bn) {
-    case 64: return launch_tma<64>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
-    case 128: return launch_tma<128>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
-    case 160: return launch_tma<160>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
-    default: return launch_tma<224>(A, lda, B, ldb, C, ldc, M, N, K, ep, st);
-  }
+  return pgnn_tma_gemm(false, false, bn, A, lda, B, ldb, C, ldc, M, N, K, 1, K, ep, st);
 }
