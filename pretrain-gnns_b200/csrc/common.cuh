@@ -54,6 +54,7 @@ struct TcEpilogue {
   int64_t ldm;
   int atomic;             // split-K: accumulate with atomics into a zeroed output
   PgnnGemmHooks hooks;    // fused column reductions over the final output tile (not with split-K)
+  int64_t split_stride = 0;  // split-K without atomics: split z stores its tile at C + z * split_stride (folded afterwards)
 };
 
 // B200: 148 SMs.  Grids for grid-stride kernels are sized as a multiple of this.

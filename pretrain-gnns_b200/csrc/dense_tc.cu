@@ -447,9 +447,35 @@ int pgnn_internal_transpose_batch(int count, const float* const* in, float* cons
   return PGNN_OK;
 }
 
-// gw[N,K] = gy[M,N]^T . x[M,K]; gb[N] = column sums of gy
+namespace {
+// out[i] = sum_s part[s][i]: folds the split-K partial tiles (plain coalesced stores from the GEMM epilogue instead of
+// ~4 M vector atomics per wgrad on the same 0.7 MB of output)
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, int64_t n4, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(part)[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = reinterpret_cast<const float4*>(part)[(int64_t)s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+}  // namespace
+
+int64_t pgnn_tc_wgrad_workspace_floats(int64_t N, int64_t K) { return (int64_t)kNumSMs * N * K / 8 + N * K; }  // generous bound: splits <= 148 / tiles
+
+// gw[N,K] = gy[M,N]^T . x[M,K]; gb[N] = column sums of gy.  `partials` (optional, >= splits*N*K floats): split-K partial
+// tiles are stored there and folded by one reduction kernel; without it the epilogue uses vector atomics.
+int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                            float* gb, float* partials, int64_t partial_floats, cudaStream_t st);
+
 int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                          float* gb, cudaStream_t st) {
+  return pgnn_tc_linear_bwd_w_ws(gy, ldgy, x, ldx, M, N, K, gw, gb, nullptr, 0, st);
+}
+
+int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                            float* gb, float* partials, int64_t partial_floats, cudaStream_t st) {
   if (N % 4 || K % 4 || ldgy % 4 || ldx % 4 || !aligned16(gy) || !aligned16(x) || !aligned16(gw) || M < 1) return PGNN_EUNSUPPORTED;
   // output [N, K] (rows N = "M" of the MMA), reduction over the M node rows, split so the grid fills the chip
   int bn = 224;  // the reduction is long and both operands are re-read per tile: widest tile with <= 15% padding
@@ -466,11 +492,27 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
   if (splits < 1) splits = 1;
   int per = (int)align_up(ceil_div(M, splits), 32);  // multiple of the TMA kernel's 32-deep block (and of BK)
   splits = (int)ceil_div(M, per);
-  if (splits > 1) PGNN_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * N * K, st));
-  TcEpilogue ep{nullptr, 0, nullptr, 0, splits > 1, PgnnGemmHooks{}};
   int rc = PGNN_EUNSUPPORTED;
-  if (tma_enabled()) rc = pgnn_tma_gemm(true, true, bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
-  if (rc == PGNN_EUNSUPPORTED) rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+  const bool two_phase = splits > 1 && partials && partial_floats >= (int64_t)splits * N * K && tma_enabled() && ((N * K) % 4 == 0);
+  if (two_phase) {
+    // split s writes its tile into partials[s] (the kernel offsets C by blockIdx.z * N * ldc through ep.split_stride)
+    TcEpilogue ep{nullptr, 0, nullptr, 0, 0, PgnnGemmHooks{}};
+    ep.split_stride = N * K;
+    rc = pgnn_tma_gemm(true, true, bn, gy, ldgy, x, ldx, partials, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+    if (rc == PGNN_OK) {
+      const int64_t n4 = N * K / 4;
+      int blocks = (int)ceil_div(n4, 256);
+      if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+      k_splitk_reduce<<<blocks, 256, 0, st>>>(partials, splits, n4, gw);
+      PGNN_LAUNCH_CHECK();
+    }
+  }
+  if (rc == PGNN_EUNSUPPORTED) {
+    if (splits > 1) PGNN_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * N * K, st));
+    TcEpilogue ep{nullptr, 0, nullptr, 0, splits > 1, PgnnGemmHooks{}};
+    if (tma_enabled()) rc = pgnn_tma_gemm(true, true, bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+    if (rc == PGNN_EUNSUPPORTED) rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+  }
   if (rc != PGNN_OK) return rc;
   if (gb) {
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));

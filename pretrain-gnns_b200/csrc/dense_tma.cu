@@ -75,6 +75,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int nkb = (kend - kbeg + TBK - 1) / TBK;
   const bool s_bias_on = ep.bias != nullptr && blockIdx.z == 0;
   for (int i = threadIdx.x; i < BN; i += T_NTHREADS) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
+  if (warp == 0) TC_TRACE(0);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -99,6 +100,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
   constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
+  if (warp == 0) TC_TRACE(1);
 
   if (warp == 9) {
     // ---------------- TMA producer ----------------
@@ -133,6 +135,8 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(smem_u32(&lo_full[kb % T_NLO]), (kb / T_NLO) & 1);
       fence_async_smem();  // the converters' generic-proxy lo stores, observed through the barrier -> async proxy
       tc_fence_after();
+      if (kb == 0) TC_TRACE(4);
+      if (kb == nkb - 1) TC_TRACE(5);
       if (lane == 0) {
         const uint32_t ah = smem_u32(raw(kb)), bh = ah + Cfg::A_BYTES, al = smem_u32(lo(kb)), bl = al + Cfg::A_BYTES;
 #pragma unroll
@@ -169,6 +173,8 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&lo_full[kb % T_NLO]));
+      if (warp == 0 && kb == 0) TC_TRACE(2);        // first block converted
+      if (warp == 0 && kb == nkb - 1) TC_TRACE(3);  // last block converted
     }
   }
   if (warp >= NPRODUCER / 32) {
@@ -178,9 +184,12 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
   tc_fence_after();
-  tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C, ldc, ep);
+  if (warp == 0) TC_TRACE(6);
+  tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
+  if (warp == 0) TC_TRACE(7);
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) TC_TRACE(8);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
   }
@@ -259,6 +268,10 @@ int pgnn_tma_gemm(bool a_mn, bool b_mn, int bn, const float* A, int64_t lda, con
   if (!a_mn && b_mn) return dispatch_tma<false, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
   if (a_mn && b_mn) return dispatch_tma<true, true>(bn, A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
   return PGNN_EUNSUPPORTED;
+}
+
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_tma_trace(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
 }
 
 int pgnn_tma_gemm_kk(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,

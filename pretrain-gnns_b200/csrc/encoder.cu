@@ -22,6 +22,9 @@ int pgnn_tc_linear_fwd(const float*, int64_t, const float*, const float*, int64_
 int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, int64_t, const float*, int64_t, float*, int64_t,
                          cudaStream_t, const PgnnGemmHooks*);
 int pgnn_tc_linear_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
+int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                            float* gb, float* partials, int64_t partial_floats, cudaStream_t st);
+int64_t pgnn_tc_wgrad_workspace_floats(int64_t N, int64_t K);
 int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int64_t M, int64_t N, int64_t K, const float* relu_src,
                             int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks);
 int pgnn_internal_transpose_batch(int count, const float* const* in, float* const* out, const int* rows, const int* cols,
@@ -58,6 +61,8 @@ struct Ws {
   float *aggr, *z1, *z2;                           // [L, N, D], [L, N, 2D], [L, N, D]
   float *gh, *gz2, *gz1, *gaggr;                   // backward temporaries
   float* wT;                                       // [L][2][2D*D]: mlp.0.weight^T, mlp.2.weight^T (dgrad B operands)
+  float* wpart;                                    // split-K partial tiles of one wgrad
+  int64_t wpart_floats;
   void* scratch;                                   // bucket / BatchNorm scratch
   int64_t scratch_bytes, total;
 };
@@ -86,6 +91,8 @@ Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.gz1 = c.take<float>(N * 2 * D);
   w.gaggr = c.take<float>(N * D);
   w.wT = c.take<float>(L * 4 * D * D);
+  w.wpart_floats = pgnn_tc_wgrad_workspace_floats(2 * D, D);
+  w.wpart = c.take<float>(w.wpart_floats);
   int64_t sb = pgnn_graph_prep_workspace_bytes(N, E);
   const int64_t bb = pgnn_bn_workspace_bytes(N > 0 ? N : 1, D);
   if (bb > sb) sb = bb;
@@ -246,7 +253,7 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
     // passes of their own: colsum(gz1) = gradient of mlp.0.bias, and S^T gaggr = gradient of the two bond tables.
     bool fused = false;
     if (precision == 1) {
-      int rc = pgnn_tc_linear_bwd_w(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, st);
+      int rc = pgnn_tc_linear_bwd_w_ws(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, w.wpart, w.wpart_floats, st);
       if (rc == PGNN_OK) {
         PGNN_CUDA(cudaMemsetAsync(grads + o[L_B1], 0, sizeof(float) * 2 * D, st));
         PgnnGemmHooks h1;
@@ -256,7 +263,7 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
         if (rc == PGNN_EUNSUPPORTED)
           rc = pgnn_tc_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1);
         if (rc != PGNN_OK) return rc;
-        rc = pgnn_tc_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], nullptr, st);
+        rc = pgnn_tc_linear_bwd_w_ws(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], nullptr, w.wpart, w.wpart_floats, st);
         if (rc != PGNN_OK) return rc;
         PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));  // the two tables are adjacent in the layout
         PgnnGemmHooks h2;

@@ -249,3 +249,39 @@ def test_value_errors_match_reference():
         chem.GNN(5, 300)(1, 2)
     with pytest.raises(ValueError):
         chem.GNN_graphpred(5, 300, 1, graph_pooling="bogus")
+
+
+def test_bio_full_size_properties_b64():
+    """BASELINE configs[3] size per GPU (B=64 PPI-ego-shaped graphs, ~32k nodes, ~320k edges): determinism and
+    graph independence (eval mode) of the bio GIN encoder; finite train-mode step."""
+    b = syn.ppi_batch(64, 77, num_tasks=8)
+    P = O.make_params("bio", "gin", 5, 300, seed=13)
+    with torch.no_grad():
+        _, o1 = _run("bio", "gin", b, P, False)
+        _, o2 = _run("bio", "gin", b, P, False)
+        assert torch.equal(o1, o2)
+        n0 = int(b["ptr"][1])
+        e0 = int((b["edge_index"][0] < n0).sum())
+        b0 = dict(x=b["x"][:n0], edge_index=b["edge_index"][:, :e0], edge_attr=b["edge_attr"][:e0])
+        _, o3 = _run("bio", "gin", b0, P, False)
+        assert torch.allclose(o3, o1[:n0], atol=1e-4, rtol=1e-4)
+    model, out = _run("bio", "gin", b, P, True)
+    out.square().mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("t", [x for x in ("gcn", "graphsage", "gat") if x in IMPLEMENTED])
+def test_config5_full_size_b256(t):
+    """BASELINE configs[4]: gnn_type sweep at B=256 — determinism, finite gradients, eval-mode graph independence."""
+    b = syn.zinc_batch(256, 43)
+    P = O.make_params("chem", t, 5, 300, seed=17)
+    with torch.no_grad():
+        _, o1 = _run("chem", t, b, P, False)
+        n0 = int(b["ptr"][1])
+        e0 = int((b["edge_index"][0] < n0).sum())
+        b0 = dict(x=b["x"][:n0], edge_index=b["edge_index"][:, :e0], edge_attr=b["edge_attr"][:e0])
+        _, o2 = _run("chem", t, b0, P, False)
+        assert torch.allclose(o2, o1[:n0], atol=1e-4, rtol=1e-4)
+    model, out = _run("chem", t, b, P, True)
+    out.square().mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())

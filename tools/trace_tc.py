@@ -14,6 +14,6 @@ for (M, N, K) in [(5986, 600, 300), (130, 600, 300), (5986, 300, 600)]:
         y = ops._linear_fwd(x, w, b, True)
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
-    dll.pgnn_debug_tc_trace(buf)
+    (dll.pgnn_debug_tc_trace if os.environ.get('PGNN_NO_TMA') == '1' else dll.pgnn_debug_tma_trace)(buf)
     t = list(buf)
     print("fwd M=%d N=%d K=%d:" % (M, N, K), " | ".join("%s +%.2fus" % (n, (t[i] - t[0]) / 1e3) for i, n in enumerate(names)))
