@@ -16,6 +16,9 @@
 //   epilogue (warps 0-7): tc_common.cuh, identical to dense_tc.cu (two accumulators, staged coalesced stores, hooks).
 #include <cuda.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -227,11 +230,40 @@ bool make_map(CUtensorMap* map, const float* base, bool mn, int64_t R, int64_t K
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Encoding a tensor map costs a few microseconds on the host and a training step needs ~60 of them (2 per GEMM), while
+// the operands recur: weights keep their addresses and the caching allocator hands the same workspace blocks back for
+// recurring batch shapes.  Memoise by (address, extents, stride, major, box).
+struct MapKey {
+  const void* base; int64_t R, K, ld; int mn, box;
+  bool operator==(const MapKey& o) const { return base == o.base && R == o.R && K == o.K && ld == o.ld && mn == o.mn && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    for (int64_t v : {k.R, k.K, k.ld, (int64_t)k.mn, (int64_t)k.box}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+bool cached_map(CUtensorMap* out, const float* base, bool mn, int64_t R, int64_t Kred, int64_t ld, int box_r) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  const MapKey key{base, R, Kred, ld, mn ? 1 : 0, box_r};
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  alignas(64) CUtensorMap m;
+  if (!make_map(&m, base, mn, R, Kred, ld, box_r)) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return true;
+}
+
 template <bool A_MN, bool B_MN, int BN>
 int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits,
                int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
   alignas(64) CUtensorMap ma, mb;
-  if (!make_map(&ma, A, A_MN, M, K, lda, BM) || !make_map(&mb, B, B_MN, N, K, ldb, BN)) return PGNN_EUNSUPPORTED;
+  if (!cached_map(&ma, A, A_MN, M, K, lda, BM) || !cached_map(&mb, B, B_MN, N, K, ldb, BN)) return PGNN_EUNSUPPORTED;
   constexpr int smem = TmaCfg<BN>::SMEM;
   static bool configured = false;
   if (!configured) {
