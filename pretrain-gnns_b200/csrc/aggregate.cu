@@ -53,6 +53,7 @@ k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restric
                 const int* __restrict__ nbr, int mode, const float* __restrict__ dinv, const float* __restrict__ S, int Q,
                 const float* __restrict__ T, const float* __restrict__ T2, int q_split, int64_t edge_off, float* __restrict__ out,
                 int64_t ldo) {
+  pdl_prologue();
   const int64_t total = n * C4;
   const int C = C4 * 4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256)
 k_aggregate_bwd(const float* __restrict__ g, int64_t ldg, int64_t n, int C4, const int* __restrict__ rowptr_s,
                 const int* __restrict__ nbr_s, int mode, const float* __restrict__ dinv, const int* __restrict__ rowptr_t,
                 float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
   const int64_t total = n * C4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(idx / C4);
@@ -151,6 +153,7 @@ constexpr int kMaxQ = 16;
 __global__ void __launch_bounds__(256)
 k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g, int64_t ldg, int64_t g_off, int64_t n,
                  int C, float* __restrict__ gT, int64_t ldt, float* __restrict__ gT2, int q_split) {
+  pdl_prologue();
   __shared__ float red[8][kMaxQ][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + lane;
@@ -184,6 +187,7 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
 __global__ void __launch_bounds__(256)
 k_chem_embed_fwd(const int64_t* __restrict__ x, const float* __restrict__ t1, const float* __restrict__ t2, int64_t n,
                  int C4, float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   const int64_t total = n * C4;
   const int C = C4 * 4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -197,6 +201,7 @@ k_chem_embed_fwd(const int64_t* __restrict__ x, const float* __restrict__ t1, co
 __global__ void __launch_bounds__(256)
 k_chem_embed_bwd(const int64_t* __restrict__ x, const float* __restrict__ g, int64_t ldg, int64_t n, int C4,
                  float* __restrict__ g1, float* __restrict__ g2) {
+  pdl_prologue();
   const int64_t total = n * C4;
   const int C = C4 * 4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -211,6 +216,7 @@ k_chem_embed_bwd(const int64_t* __restrict__ x, const float* __restrict__ g, int
 __global__ void __launch_bounds__(256)
 k_bio_embed_fwd(const float* __restrict__ x, const float* __restrict__ tab, int64_t n, int C4, float* __restrict__ out,
                 int64_t ldo) {
+  pdl_prologue();
   const int64_t total = n * C4;
   const int C = C4 * 4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -224,6 +230,7 @@ k_bio_embed_fwd(const float* __restrict__ x, const float* __restrict__ tab, int6
 __global__ void __launch_bounds__(256)
 k_bio_embed_bwd(const float* __restrict__ x, const float* __restrict__ g, int64_t ldg, int64_t n, int C,
                 float* __restrict__ gtab) {
+  pdl_prologue();
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a0 = 0.f, a1 = 0.f;
@@ -251,7 +258,7 @@ int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st) {
   if (n == 0) return PGNN_OK;
   dim3 grid((unsigned)ceil_div(n, kTblRows), (unsigned)ceil_div(C, 32));
-  k_edge_table_bwd<<<grid, 256, 0, st>>>(S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split);
+  PGNN_CUDA(pgnn_launch(k_edge_table_bwd, dim3(grid), dim3(256), 0, st, S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -270,8 +277,8 @@ int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_sca
       (in_scale && (!aligned16(in_scale) || !aligned16(in_shift))))
     return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_aggregate_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, st>>>(x, ldx, in_scale, in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t,
-                                                                  mode, dinv, S, (int)Q, T, T2, q_split, edge_off, out, ldo);
+  PGNN_CUDA(pgnn_launch(k_aggregate_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, st, x, ldx, in_scale, in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t,
+                                                                  mode, dinv, S, (int)Q, T, T2, q_split, edge_off, out, ldo));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -300,8 +307,8 @@ int pgnn_aggregate_bwd(const float* g, int64_t ldg, int64_t num_nodes, int64_t C
   PGNN_CHECK_ARG(g && rowptr_s && gx && (mode != PGNN_AGG_GCN || dinv) && (mode != PGNN_AGG_MEAN || rowptr_t));
   if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_aggregate_bwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(g, ldg, num_nodes, C4, rowptr_s, nbr_s, mode,
-                                                                                 dinv, rowptr_t, gx, ldgx);
+  PGNN_CUDA(pgnn_launch(k_aggregate_bwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, as_stream(stream), g, ldg, num_nodes, C4, rowptr_s, nbr_s, mode,
+                                                                                 dinv, rowptr_t, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -323,7 +330,7 @@ int pgnn_chem_embed_fwd(const int64_t* x, const float* tab1, const float* tab2, 
   PGNN_CHECK_ARG(x && tab1 && tab2 && out);
   if (C % 4 || ldo % 4 || !aligned16(tab1) || !aligned16(tab2) || !aligned16(out)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_chem_embed_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(x, tab1, tab2, num_nodes, C4, out, ldo);
+  PGNN_CUDA(pgnn_launch(k_chem_embed_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, as_stream(stream), x, tab1, tab2, num_nodes, C4, out, ldo));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -338,7 +345,7 @@ int pgnn_chem_embed_bwd(const int64_t* x, const float* g, int64_t ldg, int64_t n
   PGNN_CHECK_ARG(x && g);
   if (C % 4 || ldg % 4 || !aligned16(g) || !aligned16(gtab1) || !aligned16(gtab2)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_chem_embed_bwd<<<grid_items(num_nodes * C4, 256), 256, 0, st>>>(x, g, ldg, num_nodes, C4, gtab1, gtab2);
+  PGNN_CUDA(pgnn_launch(k_chem_embed_bwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, st, x, g, ldg, num_nodes, C4, gtab1, gtab2));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -349,7 +356,7 @@ int pgnn_bio_embed_fwd(const float* x, const float* tab, int64_t num_nodes, int6
   PGNN_CHECK_ARG(x && tab && out);
   if (C % 4 || ldo % 4 || !aligned16(tab) || !aligned16(out)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_bio_embed_fwd<<<grid_items(num_nodes * C4, 256), 256, 0, as_stream(stream)>>>(x, tab, num_nodes, C4, out, ldo);
+  PGNN_CUDA(pgnn_launch(k_bio_embed_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, as_stream(stream), x, tab, num_nodes, C4, out, ldo));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -361,7 +368,7 @@ int pgnn_bio_embed_bwd(const float* x, const float* g, int64_t ldg, int64_t num_
   if (num_nodes == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && g);
   dim3 grid((unsigned)(num_nodes < 64 ? num_nodes : 64), (unsigned)ceil_div(C, 256));
-  k_bio_embed_bwd<<<grid, 256, 0, st>>>(x, g, ldg, num_nodes, (int)C, gtab);
+  PGNN_CUDA(pgnn_launch(k_bio_embed_bwd, dim3(grid), dim3(256), 0, st, x, g, ldg, num_nodes, (int)C, gtab));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

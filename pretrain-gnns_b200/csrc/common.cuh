@@ -5,6 +5,7 @@
 #include "../../include/pgnn_b200.h"
 
 #include <atomic>
+#include <utility>
 extern thread_local int g_pgnn_last_cuda_error;
 extern std::atomic<long long> g_pgnn_kernel_launches;  // every kernel this library enqueues (pgnn_kernel_launch_count)
 
@@ -59,6 +60,34 @@ struct TcEpilogue {
 
 // B200: 148 SMs.  Grids for grid-stride kernels are sized as a multiple of this.
 constexpr int kNumSMs = 148;
+
+// Programmatic dependent launch (PDL).  Every kernel of this library starts with pdl_prologue(): wait until the
+// previous kernel in the stream has completed and flushed (griddepcontrol.wait), then allow the NEXT kernel's CTAs to
+// become resident (griddepcontrol.launch_dependents) so that its launch latency and prologue overlap this kernel's
+// execution; they park on their own wait.  All launches go through pgnn_launch(), which sets the
+// programmatic-stream-serialization attribute.  A step is ~85 short kernels: the ~2-3 us of drain + launch between two
+// dependent kernels was ~15% of the step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t pgnn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

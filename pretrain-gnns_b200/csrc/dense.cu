@@ -26,6 +26,7 @@ template <bool A_RC, bool B_RC>
 __global__ void __launch_bounds__(256)
 k_sgemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ Cout,
         int64_t ldc, int M, int N, int K, int k_per_split, Epilogue ep) {
+  pdl_prologue();
   // element (m, r) of A is A[m*lda + r] if A_RC else A[r*lda + m]; same for B with (n, r)
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -152,6 +153,7 @@ k_sgemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, i
 // gb[n] = sum_m gy[m][n]: grid.x = column tiles of 128, grid.y = row splits, atomics fold the splits.
 __global__ void __launch_bounds__(128)
 k_colsum(const float* __restrict__ gy, int64_t ld, int M, int N, int rows_per_split, float* __restrict__ gb) {
+  pdl_prologue();
   const int n = blockIdx.x * 128 + threadIdx.x;
   if (n >= N) return;
   const int r0 = blockIdx.y * rows_per_split, r1 = min(M, r0 + rows_per_split);
@@ -183,7 +185,7 @@ int pgnn_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bi
   }
   Epilogue ep{bias, relu, nullptr, 0, 0};
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
-  k_sgemm<true, true><<<grid, 256, 0, st>>>(x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, (int)K, ep);
+  PGNN_CUDA(pgnn_launch(k_sgemm<true, true>, dim3(grid), dim3(256), 0, st, x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, (int)K, ep));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -201,7 +203,7 @@ int pgnn_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t M, 
   // out[m, k] = sum_n gy[m, n] * w[n, k]: "N" of the template is K here, reduction runs over N
   Epilogue ep{nullptr, 0, relu_src, ldr, 0};
   dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(M, BM), 1);
-  k_sgemm<true, false><<<grid, 256, 0, st>>>(gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, (int)N, ep);
+  PGNN_CUDA(pgnn_launch(k_sgemm<true, false>, dim3(grid), dim3(256), 0, st, gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, (int)N, ep));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -232,7 +234,7 @@ int pgnn_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t ldx
   if (splits > 1) PGNN_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * N * K, st));
   Epilogue ep{nullptr, 0, nullptr, 0, splits > 1};
   dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(N, BM), (unsigned)splits);
-  k_sgemm<false, false><<<grid, 256, 0, st>>>(gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, per, ep);
+  PGNN_CUDA(pgnn_launch(k_sgemm<false, false>, dim3(grid), dim3(256), 0, st, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, per, ep));
   PGNN_LAUNCH_CHECK();
   if (gb) {
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
@@ -240,7 +242,7 @@ int pgnn_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t ldx
     if (rsplit > 64) rsplit = 64;
     const int rows_per = (int)ceil_div(M, rsplit);
     dim3 g2((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, rows_per));
-    k_colsum<<<g2, 128, 0, st>>>(gy, ldgy, (int)M, (int)N, rows_per, gb);
+    PGNN_CUDA(pgnn_launch(k_colsum, dim3(g2), dim3(128), 0, st, gy, ldgy, (int)M, (int)N, rows_per, gb));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;

@@ -174,7 +174,6 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   const int nkb = (kend - kbeg + BK - 1) / BK;
   if (warp == 0) TC_TRACE(0);
   const bool s_bias_on = ep.bias != nullptr && blockIdx.z == 0;
-  for (int i = threadIdx.x; i < BN; i += NTHREADS) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -196,6 +195,10 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
   constexpr uint32_t idesc = umma_idesc(BM, BN, !A_KC, !B_KC);
+  // everything above (TMEM allocation, barrier init) is independent of the previous kernel's output
+  pdl_prologue();
+  if (threadIdx.x < NPRODUCER)
+    for (int i = threadIdx.x; i < BN; i += NPRODUCER) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
   if (warp == 0) TC_TRACE(1);
 
   if (warp < NPRODUCER / 32) {
@@ -280,6 +283,7 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
 // gb[n] = sum_m gy[m][n]: 32 columns x 8 row-lanes per block, coalesced row sweeps, smem fold, one atomic per column
 __global__ void __launch_bounds__(256)
 k_colsum_tc(const float* __restrict__ gy, int64_t ld, int M, int N, int rows_per_block, float* __restrict__ gb) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
@@ -311,7 +315,7 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, i
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
-  k_gemm_3xtf32<A_KC, B_KC, BN><<<grid, NTHREADS, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep);
+  PGNN_CUDA(pgnn_launch(k_gemm_3xtf32<A_KC, B_KC, BN>, dim3(grid), dim3(NTHREADS), smem, st, A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -417,6 +421,7 @@ struct TransposeJob { const float* in; float* out; int rows, cols; };
 constexpr int kMaxTransposeJobs = 32;
 struct TransposeBatch { TransposeJob job[kMaxTransposeJobs]; };
 __global__ void __launch_bounds__(256) k_transpose_batch(TransposeBatch b) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const TransposeJob j = b.job[blockIdx.z];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -442,7 +447,7 @@ int pgnn_internal_transpose_batch(int count, const float* const* in, float* cons
     mc = cols[i] > mc ? cols[i] : mc;
   }
   dim3 grid((unsigned)ceil_div(mc, 32), (unsigned)ceil_div(mr, 32), (unsigned)count);
-  k_transpose_batch<<<grid, 256, 0, st>>>(b);
+  PGNN_CUDA(pgnn_launch(k_transpose_batch, dim3(grid), dim3(256), 0, st, b));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -451,6 +456,7 @@ namespace {
 // out[i] = sum_s part[s][i]: folds the split-K partial tiles (plain coalesced stores from the GEMM epilogue instead of
 // ~4 M vector atomics per wgrad on the same 0.7 MB of output)
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, int64_t n4, float* __restrict__ out) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<const float4*>(part)[i];
     for (int s = 1; s < splits; ++s) {
@@ -503,7 +509,7 @@ int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64
       const int64_t n4 = N * K / 4;
       int blocks = (int)ceil_div(n4, 256);
       if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-      k_splitk_reduce<<<blocks, 256, 0, st>>>(partials, splits, n4, gw);
+      PGNN_CUDA(pgnn_launch(k_splitk_reduce, dim3(blocks), dim3(256), 0, st, partials, splits, n4, gw));
       PGNN_LAUNCH_CHECK();
     }
   }
@@ -518,7 +524,7 @@ int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
     const int rows_per = 256;
     dim3 g2((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, rows_per));
-    k_colsum_tc<<<g2, 256, 0, st>>>(gy, ldgy, (int)M, (int)N, rows_per, gb);
+    PGNN_CUDA(pgnn_launch(k_colsum_tc, dim3(g2), dim3(256), 0, st, gy, ldgy, (int)M, (int)N, rows_per, gb));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;

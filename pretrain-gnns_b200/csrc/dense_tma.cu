@@ -77,7 +77,6 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int kend = min(K, kbeg + k_per_split);
   const int nkb = (kend - kbeg + TBK - 1) / TBK;
   const bool s_bias_on = ep.bias != nullptr && blockIdx.z == 0;
-  for (int i = threadIdx.x; i < BN; i += T_NTHREADS) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
   if (warp == 0) TC_TRACE(0);
 
   if (warp == 0) {
@@ -103,6 +102,10 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
   constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
+  // everything above (TMEM allocation, barrier init) is independent of the previous kernel's output
+  pdl_prologue();
+  if (threadIdx.x < NPRODUCER)
+    for (int i = threadIdx.x; i < BN; i += NPRODUCER) s_bias[i] = (s_bias_on && n0 + i < N) ? ep.bias[n0 + i] : 0.f;
   if (warp == 0) TC_TRACE(1);
 
   if (warp == 9) {
@@ -271,7 +274,7 @@ int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* 
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
-  k_gemm_3xtf32_tma<A_MN, B_MN, BN><<<grid, T_NTHREADS, smem, st>>>(ma, mb, C, ldc, M, N, K, k_per_split, ep);
+  PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN>, dim3(grid), dim3(T_NTHREADS), smem, st, ma, mb, C, ldc, M, N, K, k_per_split, ep));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -68,6 +68,7 @@ __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? 
 // pq[n][h] = (<att[h,:D], xl[n,h]>, <att[h,D:], xl[n,h]>), one warp per (n, h)
 __global__ void __launch_bounds__(256)
 k_gat_node_scores(const float* __restrict__ xl, int64_t n, int H, int D, const float* __restrict__ att, float* __restrict__ pq) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t total = n * H;
   for (int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += (int64_t)gridDim.x * (blockDim.x >> 5)) {
@@ -94,6 +95,7 @@ k_gat_fwd(const float* __restrict__ xl, int64_t n, int H, int D, const float* __
           const void* __restrict__ feat, const int* __restrict__ rowptr, const int* __restrict__ nbr, const int* __restrict__ eid,
           int64_t E, const float* __restrict__ bias, float slope, const float* __restrict__ pq, float* __restrict__ alpha,
           float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   constexpr int Q = BIO ? 10 : 9;
   __shared__ float sR[kQ * kMaxH];
   build_R(att, T, Q, H, D, sR);
@@ -195,6 +197,7 @@ k_gat_bwd_target(const float* __restrict__ g, int64_t ldg, const float* __restri
                  const int* __restrict__ rowptr, const int* __restrict__ nbr, const int* __restrict__ eid, int64_t E, float slope,
                  const float* __restrict__ alpha, const float* __restrict__ pq, float* __restrict__ dl_e, float* __restrict__ al_e,
                  float* __restrict__ dpq, float* __restrict__ Aout, float* __restrict__ Bsum) {
+  pdl_prologue();
   constexpr int Q = BIO ? 10 : 9;
   __shared__ float sR[kQ * kMaxH];
   build_R(att, T, Q, H, D, sR);
@@ -293,6 +296,7 @@ __global__ void __launch_bounds__(256)
 k_gat_bwd_source(const float* __restrict__ g, int64_t ldg, int64_t n, int H, int D, const float* __restrict__ att,
                  const int* __restrict__ rowptr_s, const int* __restrict__ nbr_s, const int* __restrict__ eid_s, int64_t E,
                  const float* __restrict__ dl_e, const float* __restrict__ al_e, float* __restrict__ dpq, float* __restrict__ gxl) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int HD = H * D;
   const float invH = 1.f / (float)H;
@@ -330,6 +334,7 @@ k_gat_bwd_source(const float* __restrict__ g, int64_t ldg, int64_t n, int H, int
 // the r_k = f_k . R path: gatt[h, D:] += sum_q Bsum[q,h] T[q,h,:] ;  gT[q,h,:] += Bsum[q,h] att[h, D:]
 __global__ void k_gat_bwd_rterm(const float* __restrict__ Bsum, const float* __restrict__ att, const float* __restrict__ T, int Q,
                                 int H, int D, float* __restrict__ gatt, float* __restrict__ gT) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= H * D) return;
   const int h = idx / D, c = idx % D;
@@ -345,6 +350,7 @@ __global__ void k_gat_bwd_rterm(const float* __restrict__ Bsum, const float* __r
 
 __global__ void __launch_bounds__(128)
 k_colsum_atomic(const float* __restrict__ g, int64_t ld, int64_t M, int N, int rows_per, float* __restrict__ out) {
+  pdl_prologue();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= N) return;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
@@ -394,14 +400,14 @@ int pgnn_gat_fwd(const float* xl, int64_t num_nodes, int64_t H, int64_t D, const
   if (num_nodes == 0) return PGNN_OK;
   PGNN_CHECK_ARG(xl && att && T && rowptr_t && bias && alpha && pq && out && (num_edges == 0 || (feat && nbr_t && eid_t)));
   cudaStream_t st = as_stream(stream);
-  k_gat_node_scores<<<warp_grid(num_nodes * H), 256, 0, st>>>(xl, num_nodes, (int)H, (int)D, att, pq);
+  PGNN_CUDA(pgnn_launch(k_gat_node_scores, dim3(warp_grid(num_nodes * H)), dim3(256), 0, st, xl, num_nodes, (int)H, (int)D, att, pq));
   PGNN_LAUNCH_CHECK();
   if (is_bio)
-    k_gat_fwd<true><<<warp_grid(num_nodes), 256, 0, st>>>(xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t, eid_t,
-                                                          num_edges, bias, slope, pq, alpha, out, ldo);
+    PGNN_CUDA(pgnn_launch(k_gat_fwd<true>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t, eid_t,
+                                                          num_edges, bias, slope, pq, alpha, out, ldo));
   else
-    k_gat_fwd<false><<<warp_grid(num_nodes), 256, 0, st>>>(xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t, eid_t,
-                                                           num_edges, bias, slope, pq, alpha, out, ldo);
+    PGNN_CUDA(pgnn_launch(k_gat_fwd<false>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t, eid_t,
+                                                           num_edges, bias, slope, pq, alpha, out, ldo));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -429,14 +435,14 @@ int pgnn_gat_bwd(const float* g, int64_t ldg, const float* xl, int64_t num_nodes
   BwdWs w = carve(workspace, num_nodes, num_edges, H);
   PGNN_CUDA(cudaMemsetAsync(w.Bsum, 0, sizeof(float) * kQ * kMaxH, st));
   if (is_bio)
-    k_gat_bwd_target<true><<<warp_grid(num_nodes), 256, 0, st>>>(g, ldg, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t,
-                                                                 eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum);
+    PGNN_CUDA(pgnn_launch(k_gat_bwd_target<true>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t,
+                                                                 eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum));
   else
-    k_gat_bwd_target<false><<<warp_grid(num_nodes), 256, 0, st>>>(g, ldg, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t,
-                                                                  eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum);
+    PGNN_CUDA(pgnn_launch(k_gat_bwd_target<false>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t,
+                                                                  eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum));
   PGNN_LAUNCH_CHECK();
-  k_gat_bwd_source<<<warp_grid(num_nodes), 256, 0, st>>>(g, ldg, num_nodes, (int)H, (int)D, att, rowptr_s, nbr_s, eid_s, num_edges,
-                                                         w.dl_e, w.al_e, w.dpq, gxl);
+  PGNN_CUDA(pgnn_launch(k_gat_bwd_source, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, num_nodes, (int)H, (int)D, att, rowptr_s, nbr_s, eid_s, num_edges,
+                                                         w.dl_e, w.al_e, w.dpq, gxl));
   PGNN_LAUNCH_CHECK();
   for (int h = 0; h < H; ++h) {
     // message path into the table: gT[:, h, :] = (A_h / H)^T g
@@ -447,14 +453,14 @@ int pgnn_gat_bwd(const float* g, int64_t ldg, const float* xl, int64_t num_nodes
                                       gatt + (int64_t)h * 2 * D, D, st);
     if (rc != PGNN_OK) return rc;
   }
-  k_gat_bwd_rterm<<<(unsigned)ceil_div(H * D, 128), 128, 0, st>>>(w.Bsum, att, T, Q, (int)H, (int)D, gatt, gT);
+  PGNN_CUDA(pgnn_launch(k_gat_bwd_rterm, dim3((unsigned)ceil_div(H * D, 128)), dim3(128), 0, st, w.Bsum, att, T, Q, (int)H, (int)D, gatt, gT));
   PGNN_LAUNCH_CHECK();
   {
     int64_t splits = ceil_div(num_nodes, 256);
     if (splits > 64) splits = 64;
     const int rows_per = (int)ceil_div(num_nodes, splits);
     dim3 grid((unsigned)ceil_div(D, 128), (unsigned)ceil_div(num_nodes, rows_per));
-    k_colsum_atomic<<<grid, 128, 0, st>>>(g, ldg, num_nodes, (int)D, rows_per, gbias);
+    PGNN_CUDA(pgnn_launch(k_colsum_atomic, dim3(grid), dim3(128), 0, st, g, ldg, num_nodes, (int)D, rows_per, gbias));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;

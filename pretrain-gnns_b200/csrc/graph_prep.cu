@@ -9,6 +9,7 @@
 namespace {
 
 __global__ void k_histogram(const int64_t* __restrict__ keys, int64_t stride, int64_t n, int* __restrict__ counts) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     atomicAdd(&counts[keys[i * stride]], 1);
 }
@@ -18,6 +19,7 @@ __global__ void k_histogram(const int64_t* __restrict__ keys, int64_t stride, in
 // here are node / graph / vocabulary counts (<= a few 10^5), so one CTA is latency- not throughput-bound.
 __global__ void __launch_bounds__(1024) k_exclusive_scan(const int* counts, int64_t n,
                                                          int* rowptr, int* cursor) {
+  pdl_prologue();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const int* counts, int6
 
 __global__ void k_place(const int64_t* __restrict__ keys, int64_t stride, int64_t n, int* __restrict__ cursor,
                         int* __restrict__ tmp) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int pos = atomicAdd(&cursor[keys[i * stride]], 1);
     tmp[pos] = (int)i;
@@ -72,6 +75,7 @@ __global__ void k_rank_in_bucket(const int64_t* __restrict__ keys, int64_t strid
                                  const int* __restrict__ rowptr, const int* __restrict__ tmp,
                                  const int64_t* __restrict__ vals, int64_t val_stride, int* __restrict__ order,
                                  int* __restrict__ vals_out) {
+  pdl_prologue();
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     const int me = tmp[p];
     const int64_t b = keys[(int64_t)me * stride];
@@ -84,6 +88,7 @@ __global__ void k_rank_in_bucket(const int64_t* __restrict__ keys, int64_t strid
 }
 
 __global__ void k_gcn_dinv(const int* __restrict__ rowptr, int64_t n, float* __restrict__ dinv) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     // deg.pow(-0.5) over the loop-augmented edges: in-degree + 1 >= 1, never inf (chem/model.py:78-80)
     float deg = (float)(rowptr[i + 1] - rowptr[i] + 1);
@@ -94,6 +99,7 @@ __global__ void k_gcn_dinv(const int* __restrict__ rowptr, int64_t n, float* __r
 __global__ void k_chem_edge_summary(const int64_t* __restrict__ edge_attr, const int* __restrict__ rowptr,
                                     const int* __restrict__ nbr, const int* __restrict__ eid, int64_t n, int mode,
                                     const float* __restrict__ dinv, float* __restrict__ S) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s[9];
 #pragma unroll
@@ -119,6 +125,7 @@ __global__ void k_chem_edge_summary(const int64_t* __restrict__ edge_attr, const
 __global__ void k_bio_edge_summary(const float* __restrict__ edge_attr, const int* __restrict__ rowptr,
                                    const int* __restrict__ nbr, const int* __restrict__ eid, int64_t n, int mode,
                                    const float* __restrict__ dinv, float* __restrict__ S) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s[10];
 #pragma unroll
@@ -168,16 +175,16 @@ int pgnn_bucket(const int64_t* keys, int64_t key_stride, int64_t num_keys, int64
   int* tmp = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + align_up((num_buckets + 1) * 4, 256));
   PGNN_CUDA(cudaMemsetAsync(counts, 0, (num_buckets + 1) * 4, st));
   if (num_keys > 0) {
-    k_histogram<<<grid_for(num_keys, 256), 256, 0, st>>>(keys, key_stride, num_keys, counts);
+    PGNN_CUDA(pgnn_launch(k_histogram, dim3(grid_for(num_keys, 256)), dim3(256), 0, st, keys, key_stride, num_keys, counts));
     PGNN_LAUNCH_CHECK();
   }
-  k_exclusive_scan<<<1, 1024, 0, st>>>(counts, num_buckets, rowptr, counts);
+  PGNN_CUDA(pgnn_launch(k_exclusive_scan, dim3(1), dim3(1024), 0, st, counts, num_buckets, rowptr, counts));
   PGNN_LAUNCH_CHECK();
   if (num_keys > 0) {
-    k_place<<<grid_for(num_keys, 256), 256, 0, st>>>(keys, key_stride, num_keys, counts, tmp);
+    PGNN_CUDA(pgnn_launch(k_place, dim3(grid_for(num_keys, 256)), dim3(256), 0, st, keys, key_stride, num_keys, counts, tmp));
     PGNN_LAUNCH_CHECK();
-    k_rank_in_bucket<<<grid_for(num_keys, 256), 256, 0, st>>>(keys, key_stride, num_keys, rowptr, tmp, vals,
-                                                              val_stride, order, vals_out);
+    PGNN_CUDA(pgnn_launch(k_rank_in_bucket, dim3(grid_for(num_keys, 256)), dim3(256), 0, st, keys, key_stride, num_keys, rowptr, tmp, vals,
+                                                              val_stride, order, vals_out));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;
@@ -202,7 +209,7 @@ int pgnn_graph_prep(const int64_t* edge_index, int64_t num_edges, int64_t num_no
 int pgnn_gcn_dinv(const int32_t* rowptr_t, int64_t num_nodes, float* dinv, void* stream) {
   PGNN_CHECK_ARG(num_nodes >= 0 && (num_nodes == 0 || (rowptr_t && dinv)));
   if (num_nodes == 0) return PGNN_OK;
-  k_gcn_dinv<<<grid_for(num_nodes, 256), 256, 0, as_stream(stream)>>>(rowptr_t, num_nodes, dinv);
+  PGNN_CUDA(pgnn_launch(k_gcn_dinv, dim3(grid_for(num_nodes, 256)), dim3(256), 0, as_stream(stream), rowptr_t, num_nodes, dinv));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -212,8 +219,8 @@ int pgnn_chem_edge_summary(const int64_t* edge_attr, const int32_t* rowptr_t, co
   PGNN_CHECK_ARG(num_nodes >= 0 && mode >= 0 && mode <= 2 && (mode != PGNN_AGG_GCN || dinv));
   if (num_nodes == 0) return PGNN_OK;
   PGNN_CHECK_ARG(rowptr_t && S);
-  k_chem_edge_summary<<<grid_for(num_nodes, 128), 128, 0, as_stream(stream)>>>(edge_attr, rowptr_t, nbr_t, eid_t, num_nodes,
-                                                                               mode, dinv, S);
+  PGNN_CUDA(pgnn_launch(k_chem_edge_summary, dim3(grid_for(num_nodes, 128)), dim3(128), 0, as_stream(stream), edge_attr, rowptr_t, nbr_t, eid_t, num_nodes,
+                                                                               mode, dinv, S));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -223,8 +230,8 @@ int pgnn_bio_edge_summary(const float* edge_attr, const int32_t* rowptr_t, const
   PGNN_CHECK_ARG(num_nodes >= 0 && mode >= 0 && mode <= 2 && (mode != PGNN_AGG_GCN || dinv));
   if (num_nodes == 0) return PGNN_OK;
   PGNN_CHECK_ARG(rowptr_t && S);
-  k_bio_edge_summary<<<grid_for(num_nodes, 128), 128, 0, as_stream(stream)>>>(edge_attr, rowptr_t, nbr_t, eid_t, num_nodes,
-                                                                              mode, dinv, S);
+  PGNN_CUDA(pgnn_launch(k_bio_edge_summary, dim3(grid_for(num_nodes, 128)), dim3(128), 0, as_stream(stream), edge_attr, rowptr_t, nbr_t, eid_t, num_nodes,
+                                                                              mode, dinv, S));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -13,6 +13,7 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 __global__ void __launch_bounds__(256)
 k_segment_mean_fwd(const float* __restrict__ x, int64_t ldx, const int* __restrict__ seg_ptr, const int* __restrict__ seg_order,
                    int64_t num_seg, int C4, float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   const int64_t total = num_seg * C4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = idx / C4;
@@ -31,6 +32,7 @@ k_segment_mean_fwd(const float* __restrict__ x, int64_t ldx, const int* __restri
 __global__ void __launch_bounds__(256)
 k_segment_mean_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ seg, const int* __restrict__ seg_ptr,
                    int64_t n, int C4, float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
   const int64_t total = n * C4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C4;
@@ -45,6 +47,7 @@ k_segment_mean_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __re
 __global__ void __launch_bounds__(256)
 k_row_gather_fwd(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
                  int64_t m, int C4, float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   const int64_t total = m * C4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C4;
@@ -63,6 +66,7 @@ k_row_gather_fwd(const float* __restrict__ x, int64_t ldx, const int64_t* __rest
 __global__ void __launch_bounds__(256)
 k_row_gather_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
                  int64_t m, int C4, float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
   const int64_t total = m * C4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C4;
@@ -77,6 +81,7 @@ k_row_gather_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __rest
 __global__ void __launch_bounds__(256)
 k_shifted_rowdot_fwd(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb, int64_t B, int C,
                      int64_t shift, float* __restrict__ out) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < B; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int64_t rb = (r + shift) % B;
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(256)
 k_shifted_rowdot_bwd(const float* __restrict__ g, const float* __restrict__ a, int64_t lda, const float* __restrict__ b,
                      int64_t ldb, int64_t B, int C, int64_t shift, int accumulate, float* __restrict__ ga, int64_t ldga,
                      float* __restrict__ gb, int64_t ldgb) {
+  pdl_prologue();
   const int64_t total = B * C;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C;
@@ -128,8 +134,8 @@ int pgnn_segment_mean_fwd(const float* x, int64_t ldx, const int32_t* seg_ptr, c
   PGNN_CHECK_ARG(seg_ptr && out);
   if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_segment_mean_fwd<<<grid_items(num_seg * C4, 256), 256, 0, as_stream(stream)>>>(x, ldx, seg_ptr, seg_order, num_seg, C4, out,
-                                                                                   ldo);
+  PGNN_CUDA(pgnn_launch(k_segment_mean_fwd, dim3(grid_items(num_seg * C4, 256)), dim3(256), 0, as_stream(stream), x, ldx, seg_ptr, seg_order, num_seg, C4, out,
+                                                                                   ldo));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -141,7 +147,7 @@ int pgnn_segment_mean_bwd(const float* g, int64_t ldg, const int64_t* seg, const
   PGNN_CHECK_ARG(g && seg && seg_ptr && gx);
   if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_segment_mean_bwd<<<grid_items(num_rows * C4, 256), 256, 0, as_stream(stream)>>>(g, ldg, seg, seg_ptr, num_rows, C4, gx, ldgx);
+  PGNN_CUDA(pgnn_launch(k_segment_mean_bwd, dim3(grid_items(num_rows * C4, 256)), dim3(256), 0, as_stream(stream), g, ldg, seg, seg_ptr, num_rows, C4, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -153,7 +159,7 @@ int pgnn_row_gather_fwd(const float* x, int64_t ldx, const int64_t* idx, const i
   PGNN_CHECK_ARG(x && idx && out);
   if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_row_gather_fwd<<<grid_items(num_idx * C4, 256), 256, 0, as_stream(stream)>>>(x, ldx, idx, idx2, num_idx, C4, out, ldo);
+  PGNN_CUDA(pgnn_launch(k_row_gather_fwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), x, ldx, idx, idx2, num_idx, C4, out, ldo));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -165,7 +171,7 @@ int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const i
   PGNN_CHECK_ARG(g && idx && gx);
   if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  k_row_gather_bwd<<<grid_items(num_idx * C4, 256), 256, 0, as_stream(stream)>>>(g, ldg, idx, idx2, num_idx, C4, gx, ldgx);
+  PGNN_CUDA(pgnn_launch(k_row_gather_bwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), g, ldg, idx, idx2, num_idx, C4, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -175,7 +181,7 @@ int pgnn_shifted_rowdot_fwd(const float* a, int64_t lda, const float* b, int64_t
   PGNN_CHECK_ARG(B >= 0 && C > 0 && shift >= 0);
   if (B == 0) return PGNN_OK;
   PGNN_CHECK_ARG(a && b && out);
-  k_shifted_rowdot_fwd<<<grid_items(B * 32, 256), 256, 0, as_stream(stream)>>>(a, lda, b, ldb, B, (int)C, shift, out);
+  PGNN_CUDA(pgnn_launch(k_shifted_rowdot_fwd, dim3(grid_items(B * 32, 256)), dim3(256), 0, as_stream(stream), a, lda, b, ldb, B, (int)C, shift, out));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -185,8 +191,8 @@ int pgnn_shifted_rowdot_bwd(const float* g, const float* a, int64_t lda, const f
   PGNN_CHECK_ARG(B >= 0 && C > 0 && shift >= 0);
   if (B == 0) return PGNN_OK;
   PGNN_CHECK_ARG(g && a && b && ga && gb);
-  k_shifted_rowdot_bwd<<<grid_items(B * C, 256), 256, 0, as_stream(stream)>>>(g, a, lda, b, ldb, B, (int)C, shift, accumulate, ga,
-                                                                             ldga, gb, ldgb);
+  PGNN_CUDA(pgnn_launch(k_shifted_rowdot_bwd, dim3(grid_items(B * C, 256)), dim3(256), 0, as_stream(stream), g, a, lda, b, ldb, B, (int)C, shift, accumulate, ga,
+                                                                             ldga, gb, ldgb));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -42,6 +42,7 @@ __device__ __forceinline__ void column_pair_sums(int M, int C, double* __restric
 
 __global__ void __launch_bounds__(256)
 k_bn_stats(const float* __restrict__ x, int64_t ldx, int M, int C, double* __restrict__ acc) {
+  pdl_prologue();
   column_pair_sums(M, C, acc, [&](int r, int c, double& a, double& b) {
     const double v = (double)x[(int64_t)r * ldx + c];
     a = v;
@@ -54,6 +55,7 @@ k_bn_finalize(const double* __restrict__ acc, int M, int C, const float* __restr
               float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ nbt, float momentum,
               float eps, float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ scale,
               float* __restrict__ shift) {
+  pdl_prologue();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256)
 k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const float* __restrict__ mean,
            const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
            float* __restrict__ y, int64_t ldy) {
+  pdl_prologue();
   const int64_t total = M * C;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C;
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256)
 k_bn_eval(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const float* __restrict__ gamma,
           const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps, int relu,
           float* __restrict__ y, int64_t ldy) {
+  pdl_prologue();
   const int64_t total = M * C;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C;
@@ -110,6 +114,7 @@ __global__ void __launch_bounds__(256)
 k_bn_bwd_stats(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                const float* __restrict__ invstd, int relu, double* __restrict__ acc) {
+  pdl_prologue();
   column_pair_sums(M, C, acc, [&](int r, int c, double& a, double& b) {
     const float xhat = (x[(int64_t)r * ldx + c] - mean[c]) * invstd[c];
     float d = gy[(int64_t)r * ldgy + c];
@@ -122,6 +127,7 @@ k_bn_bwd_stats(const float* __restrict__ gy, int64_t ldgy, const float* __restri
 __global__ void __launch_bounds__(128)
 k_bn_bwd_finalize(const double* __restrict__ acc, int M, int C, float* __restrict__ ggamma, float* __restrict__ gbeta,
                   float* __restrict__ c1, float* __restrict__ c2) {
+  pdl_prologue();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= C) return;
   const double s = acc[c], sx = acc[(int64_t)C + c];
@@ -136,6 +142,7 @@ k_bn_bwd_apply(const float* __restrict__ gy, int64_t ldgy, const float* __restri
                const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                const float* __restrict__ invstd, int relu, const float* __restrict__ c1, const float* __restrict__ c2,
                float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
   const int64_t total = M * C;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C;
@@ -154,6 +161,7 @@ k_bn_bwd_apply_colsum(const float* __restrict__ gy, int64_t ldgy, const float* _
                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                       const float* __restrict__ invstd, int relu, const float* __restrict__ c1, const float* __restrict__ c2,
                       float* __restrict__ gx, int64_t ldgx, float* __restrict__ colsum) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -183,6 +191,7 @@ k_bn_bwd_apply_colsum(const float* __restrict__ gy, int64_t ldgy, const float* _
 
 __global__ void __launch_bounds__(256)
 k_relu_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy) {
+  pdl_prologue();
   const int64_t total = M * C;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C;
@@ -193,6 +202,7 @@ k_relu_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __
 __global__ void __launch_bounds__(256)
 k_relu_bwd(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ y, int64_t ldy, int64_t M, int C,
            float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
   const int64_t total = M * C;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C;
@@ -205,6 +215,7 @@ k_relu_bwd(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__
 __global__ void __launch_bounds__(256)
 k_l2norm_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy,
              float* __restrict__ norm) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     float ss = 0.f;
@@ -218,6 +229,7 @@ k_l2norm_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* 
 __global__ void __launch_bounds__(256)
 k_l2norm_bwd(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ y, int64_t ldy, const float* __restrict__ norm,
              int64_t M, int C, float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     float dot = 0.f;
@@ -248,11 +260,11 @@ int pgnn_internal_bn_fwd_from_stats(const double* acc, const float* x, int64_t l
                                     const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
                                     float eps, int relu, float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale,
                                     float* shift, cudaStream_t st) {
-  k_bn_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, gamma, beta, running_mean, running_var, nbt,
-                                                           momentum, eps, save_mean, save_invstd, scale, shift);
+  PGNN_CUDA(pgnn_launch(k_bn_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, gamma, beta, running_mean, running_var, nbt,
+                                                           momentum, eps, save_mean, save_invstd, scale, shift));
   PGNN_LAUNCH_CHECK();
   if (y) {
-    k_bn_apply<<<grid_items(M * C, 256), 256, 0, st>>>(x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy);
+    PGNN_CUDA(pgnn_launch(k_bn_apply, dim3(grid_items(M * C, 256)), dim3(256), 0, st, x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;
@@ -268,12 +280,12 @@ int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, i
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   PGNN_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, st));
   dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
-  k_bn_bwd_stats<<<g1, 256, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc);
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_stats, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
   PGNN_LAUNCH_CHECK();
-  k_bn_bwd_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, ggamma, gbeta, c1, c2);
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, ggamma, gbeta, c1, c2));
   PGNN_LAUNCH_CHECK();
-  k_bn_bwd_apply_colsum<<<g1, 256, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, c1, c2, gx,
-                                            ldgx, colsum);
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_apply_colsum, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, c1, c2, gx,
+                                            ldgx, colsum));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -296,14 +308,14 @@ int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const f
   double* acc = reinterpret_cast<double*>(workspace);
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
-  k_bn_stats<<<g1, 256, 0, st>>>(x, ldx, (int)M, (int)C, acc);
+  PGNN_CUDA(pgnn_launch(k_bn_stats, dim3(g1), dim3(256), 0, st, x, ldx, (int)M, (int)C, acc));
   PGNN_LAUNCH_CHECK();
-  k_bn_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, gamma, beta, running_mean, running_var,
+  PGNN_CUDA(pgnn_launch(k_bn_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, gamma, beta, running_mean, running_var,
                                                            num_batches_tracked, momentum, eps, save_mean, save_invstd, scale,
-                                                           shift);
+                                                           shift));
   PGNN_LAUNCH_CHECK();
   if (y) {
-    k_bn_apply<<<grid_items(M * C, 256), 256, 0, st>>>(x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy);
+    PGNN_CUDA(pgnn_launch(k_bn_apply, dim3(grid_items(M * C, 256)), dim3(256), 0, st, x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;
@@ -315,8 +327,8 @@ int pgnn_bn_fwd_eval(const float* x, int64_t ldx, int64_t M, int64_t C, const fl
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && gamma && beta && running_mean && running_var && y);
-  k_bn_eval<<<grid_items(M * C, 256), 256, 0, as_stream(stream)>>>(x, ldx, M, (int)C, gamma, beta, running_mean, running_var, eps,
-                                                                    relu, y, ldy);
+  PGNN_CUDA(pgnn_launch(k_bn_eval, dim3(grid_items(M * C, 256)), dim3(256), 0, as_stream(stream), x, ldx, M, (int)C, gamma, beta, running_mean, running_var, eps,
+                                                                    relu, y, ldy));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -332,12 +344,12 @@ int pgnn_bn_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int6
   float* c2 = c1 + C;
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
-  k_bn_bwd_stats<<<g1, 256, 0, st>>>(gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc);
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_stats, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
   PGNN_LAUNCH_CHECK();
-  k_bn_bwd_finalize<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(acc, (int)M, (int)C, ggamma, gbeta, c1, c2);
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, ggamma, gbeta, c1, c2));
   PGNN_LAUNCH_CHECK();
-  k_bn_bwd_apply<<<grid_items(M * C, 256), 256, 0, st>>>(gy, ldgy, x, ldx, M, (int)C, gamma, beta, save_mean, save_invstd, relu,
-                                                        c1, c2, gx, ldgx);
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_apply, dim3(grid_items(M * C, 256)), dim3(256), 0, st, gy, ldgy, x, ldx, M, (int)C, gamma, beta, save_mean, save_invstd, relu,
+                                                        c1, c2, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -346,7 +358,7 @@ int pgnn_relu_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y, i
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && y);
-  k_relu_fwd<<<grid_items(M * C, 256), 256, 0, as_stream(stream)>>>(x, ldx, M, (int)C, y, ldy);
+  PGNN_CUDA(pgnn_launch(k_relu_fwd, dim3(grid_items(M * C, 256)), dim3(256), 0, as_stream(stream), x, ldx, M, (int)C, y, ldy));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -356,7 +368,7 @@ int pgnn_relu_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_, i
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(gy && y && gx);
-  k_relu_bwd<<<grid_items(M * C, 256), 256, 0, as_stream(stream)>>>(gy, ldgy, y, ldy_, M, (int)C, gx, ldgx);
+  PGNN_CUDA(pgnn_launch(k_relu_bwd, dim3(grid_items(M * C, 256)), dim3(256), 0, as_stream(stream), gy, ldgy, y, ldy_, M, (int)C, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -365,7 +377,7 @@ int pgnn_l2norm_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y,
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && y && norm);
-  k_l2norm_fwd<<<grid_items(M * 32, 256), 256, 0, as_stream(stream)>>>(x, ldx, M, (int)C, y, ldy, norm);
+  PGNN_CUDA(pgnn_launch(k_l2norm_fwd, dim3(grid_items(M * 32, 256)), dim3(256), 0, as_stream(stream), x, ldx, M, (int)C, y, ldy, norm));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -375,7 +387,7 @@ int pgnn_l2norm_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_,
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(gy && y && norm && gx);
-  k_l2norm_bwd<<<grid_items(M * 32, 256), 256, 0, as_stream(stream)>>>(gy, ldgy, y, ldy_, norm, M, (int)C, gx, ldgx);
+  PGNN_CUDA(pgnn_launch(k_l2norm_bwd, dim3(grid_items(M * 32, 256)), dim3(256), 0, as_stream(stream), gy, ldgy, y, ldy_, norm, M, (int)C, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
