@@ -52,10 +52,17 @@ k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restric
                 const float* __restrict__ in_shift, int in_relu, int64_t n, int C4, const int* __restrict__ rowptr,
                 const int* __restrict__ nbr, int mode, const float* __restrict__ dinv, const float* __restrict__ S, int Q,
                 const float* __restrict__ T, const float* __restrict__ T2, int q_split, int64_t edge_off, float* __restrict__ out,
-                int64_t ldo) {
+                int64_t ldo, PgnnBnFold fold) {
   pdl_prologue();
   const int64_t total = n * C4;
   const int C = C4 * 4;
+  extern __shared__ __align__(16) float s_aff[];  // [2][C] scale/shift when the producer's BatchNorm is folded in
+  if (fold.acc) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) bn_fold_column(fold, C, c, blockIdx.x == 0, s_aff[c], s_aff[C + c]);
+    __syncthreads();
+    in_scale = s_aff;
+    in_shift = s_aff + C;
+  }
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / C4);
     const int c = (int)(idx - (int64_t)i * C4) * 4;
@@ -271,14 +278,15 @@ int pgnn_internal_edge_table_bwd(const float* S, int Q, const float* g, int64_t 
 int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
                                 int64_t num_nodes, int64_t C, const int32_t* rowptr_t, const int32_t* nbr_t, int mode, const float* dinv,
                                 const float* S, int64_t Q, const float* T, const float* T2, int q_split, int64_t edge_off, float* out,
-                                int64_t ldo, cudaStream_t st) {
+                                int64_t ldo, cudaStream_t st, const PgnnBnFold* fold) {
   if (num_nodes == 0) return PGNN_OK;
   if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out) || (T && !aligned16(T)) || (T2 && !aligned16(T2)) ||
       (in_scale && (!aligned16(in_scale) || !aligned16(in_shift))))
     return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  PGNN_CUDA(pgnn_launch(k_aggregate_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, st, x, ldx, in_scale, in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t,
-                                                                  mode, dinv, S, (int)Q, T, T2, q_split, edge_off, out, ldo));
+  PGNN_CUDA(pgnn_launch(k_aggregate_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), fold ? sizeof(float) * 2 * C : 0, st, x, ldx, in_scale,
+                        in_shift, in_relu, num_nodes, C4, rowptr_t, nbr_t, mode, dinv, S, (int)Q, T, T2, q_split, edge_off, out, ldo,
+                        fold ? *fold : PgnnBnFold{}));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -296,7 +304,7 @@ int pgnn_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const
   PGNN_CHECK_ARG(!S || (T && Q > 0 && Q <= kMaxQ));
   PGNN_CHECK_ARG(edge_off == 0 || (S && edge_off % 4 == 0));
   return pgnn_internal_aggregate_fwd(x, ldx, in_scale, in_shift, in_relu, num_nodes, C, rowptr_t, nbr_t, mode, dinv, S, Q, T, nullptr,
-                                     (int)Q, edge_off, out, ldo, as_stream(stream));
+                                     (int)Q, edge_off, out, ldo, as_stream(stream), nullptr);
 }
 
 int pgnn_aggregate_bwd(const float* g, int64_t ldg, int64_t num_nodes, int64_t C, const int32_t* rowptr_s,

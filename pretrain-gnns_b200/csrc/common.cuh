@@ -47,6 +47,43 @@ struct PgnnGemmHooks {
   bool any() const { return colsum || stats || S; }
 };
 
+// BatchNorm finalisation folded into the consumer kernel: from the fp64 column sums `acc` ([2][C]: sum, sum of squares
+// over M rows) every CTA derives scale/shift itself; CTA 0 also performs the module-state updates of torch.nn.BatchNorm1d.
+struct PgnnBnFold {
+  const double* acc = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float* running_mean = nullptr;
+  float* running_var = nullptr;
+  int64_t* nbt = nullptr;
+  float* save_mean = nullptr;
+  float* save_invstd = nullptr;
+  float momentum = 0.1f, eps = 1e-5f;
+  int M = 0;
+};
+
+// per-column BatchNorm constants from the accumulated sums; `leader` performs the running-statistics side effects
+__device__ __forceinline__ void bn_fold_column(const PgnnBnFold& f, int C, int c, bool leader, float& scale, float& shift) {
+  const double s = f.acc[c], ss = f.acc[(int64_t)C + c];
+  const double mean = s / f.M;
+  double var = ss / f.M - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+  const float meanf = (float)mean;
+  scale = f.gamma[c] * invstd;
+  shift = fmaf(-meanf, scale, f.beta[c]);
+  if (leader) {
+    if (f.save_mean) f.save_mean[c] = meanf;
+    if (f.save_invstd) f.save_invstd[c] = invstd;
+    if (f.running_mean) f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * meanf;
+    if (f.running_var) {
+      const double unbiased = var * ((double)f.M / (double)(f.M > 1 ? f.M - 1 : 1));
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+    }
+    if (c == 0 && f.nbt) *f.nbt += 1;
+  }
+}
+
 // Epilogue of the tensor-core GEMM kernels (dense_tc.cu, dense_tma.cu)
 struct TcEpilogue {
   const float* bias;      // [N] or null

@@ -326,6 +326,10 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, i
 //     least work per CTA, most SMs busy;
 //   * otherwise (many waves) operand re-reads dominate: take the widest width with <= 15% padding waste.
 inline int pick_bn(int M, int N, int splits) {
+  if (const char* e = getenv("PGNN_BN")) {  // development override
+    const int v = atoi(e);
+    if (v == 64 || v == 128 || v == 160 || v == 224) return v;
+  }
   const int cand[4] = {64, 128, 160, 224};
   const int64_t mt = ceil_div(M, BM) * (splits > 0 ? splits : 1);
   for (int bn : cand)

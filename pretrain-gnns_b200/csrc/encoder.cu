@@ -15,7 +15,7 @@ int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t
 int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
                                 int64_t num_nodes, int64_t C, const int32_t* rowptr_t, const int32_t* nbr_t, int mode, const float* dinv,
                                 const float* S, int64_t Q, const float* T, const float* T2, int q_split, int64_t edge_off, float* out,
-                                int64_t ldo, cudaStream_t st);
+                                int64_t ldo, cudaStream_t st, const PgnnBnFold* fold);
 
 int pgnn_tc_linear_fwd(const float*, int64_t, const float*, const float*, int64_t, int64_t, int64_t, int, float*, int64_t,
                        cudaStream_t, const PgnnGemmHooks*);
@@ -29,10 +29,8 @@ int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int6
                             int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks);
 int pgnn_internal_transpose_batch(int count, const float* const* in, float* const* out, const int* rows, const int* cols,
                                   cudaStream_t st);
-int pgnn_internal_bn_fwd_from_stats(const double* acc, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
-                                    const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
-                                    float eps, int relu, float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale,
-                                    float* shift, cudaStream_t st);
+int pgnn_internal_bn_apply_fold(const float* x, int64_t ldx, int64_t M, int64_t C, const PgnnBnFold& fold, int relu, float* y,
+                                int64_t ldy, cudaStream_t st);
 int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
                                 const float* beta, const float* save_mean, const float* save_invstd, int relu, float* gx,
                                 int64_t ldgx, float* ggamma, float* gbeta, float* colsum, void* workspace, cudaStream_t st);
@@ -153,19 +151,24 @@ int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mea
   TRY(pgnn_chem_embed_fwd(x, (const float*)params[P_XEMB1], (const float*)params[P_XEMB2], N, D, w.h0, D, stream));
   const float* h = w.h0;            // input rows of the current layer (pre-affine)
   const float *in_scale = nullptr, *in_shift = nullptr;
+  PgnnBnFold fold;                  // pending BatchNorm finalisation of the previous layer (folded into this layer's gather)
+  bool have_fold = false;
+  double* const bn_acc = reinterpret_cast<double*>(w.gz1);  // [L][2][D] fp64 sums; gz1 is a backward-only buffer
   for (int64_t l = 0; l < L; ++l) {
     const void* const* p = params + P_LAYER0 + l * L_COUNT;
     float* aggr = w.aggr + l * N * D;
     float* z1 = w.z1 + l * N * 2 * D;
     float* z2 = w.z2 + l * N * D;
     const bool last = (l == L - 1);
-    TRY(pgnn_internal_aggregate_fwd(h, D, in_scale, in_shift, in_scale != nullptr, N, D, w.rowptr_t, w.nbr_t, PGNN_AGG_SUM, nullptr, w.S, 9,
-                                    (const float*)p[L_ET1], (const float*)p[L_ET2], 6, 0, aggr, D, as_stream(stream)));
+    TRY(pgnn_internal_aggregate_fwd(h, D, in_scale, in_shift, in_scale != nullptr || have_fold, N, D, w.rowptr_t, w.nbr_t, PGNN_AGG_SUM,
+                                    nullptr, w.S, 9, (const float*)p[L_ET1], (const float*)p[L_ET2], 6, 0, aggr, D, as_stream(stream),
+                                    have_fold ? &fold : nullptr));
+    have_fold = false;
     TRY(pgnn_linear_fwd(aggr, D, (const float*)p[L_W1], (const float*)p[L_B1], N, 2 * D, D, 1, z1, 2 * D, precision, stream));
     // GEMM2; on the tensor path its epilogue also accumulates the BatchNorm batch statistics of z2 (fp64 atomics)
     bool stats_fused = false;
+    double* acc = bn_acc + l * 2 * D;
     if (training && precision == 1) {
-      double* acc = reinterpret_cast<double*>(w.scratch);
       PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * D, as_stream(stream)));
       PgnnGemmHooks hk;
       hk.stats = acc;
@@ -176,14 +179,20 @@ int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mea
     if (!stats_fused)
       TRY(pgnn_linear_fwd(z1, 2 * D, (const float*)p[L_W2], (const float*)p[L_B2], N, D, 2 * D, 0, z2, D, precision, stream));
     if (training && stats_fused) {
-      TRY(pgnn_internal_bn_fwd_from_stats(reinterpret_cast<double*>(w.scratch), z2, D, N, D, (const float*)p[L_GAMMA],
-                                          (const float*)p[L_BETA], (float*)bn_running_mean[l], (float*)bn_running_var[l],
-                                          bn_num_batches_tracked ? (int64_t*)bn_num_batches_tracked[l] : nullptr, momentum, eps, 0,
-                                          last ? node_rep : nullptr, ld_out, w.mean + l * D, w.invstd + l * D, w.scale + l * D,
-                                          w.shift + l * D, as_stream(stream)));
+      // no finalize launch: the consumer (next layer's gather, or the final apply) derives scale/shift from the sums
+      fold = PgnnBnFold{};
+      fold.acc = acc; fold.gamma = (const float*)p[L_GAMMA]; fold.beta = (const float*)p[L_BETA];
+      fold.running_mean = (float*)bn_running_mean[l]; fold.running_var = (float*)bn_running_var[l];
+      fold.nbt = bn_num_batches_tracked ? (int64_t*)bn_num_batches_tracked[l] : nullptr;
+      fold.save_mean = w.mean + l * D; fold.save_invstd = w.invstd + l * D;
+      fold.momentum = momentum; fold.eps = eps; fold.M = (int)N;
+      if (last) {
+        TRY(pgnn_internal_bn_apply_fold(z2, D, N, D, fold, 0, node_rep, ld_out, as_stream(stream)));
+      } else {
+        have_fold = true;
+      }
       h = z2;
-      in_scale = w.scale + l * D;
-      in_shift = w.shift + l * D;
+      in_scale = in_shift = nullptr;
     } else if (training) {
       // statistics only for inner layers (applied on load by the next gather); the last layer materialises node_rep
       TRY(pgnn_bn_fwd_train(z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], (float*)bn_running_mean[l],

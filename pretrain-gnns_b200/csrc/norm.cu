@@ -94,6 +94,24 @@ k_bn_apply(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const flo
   }
 }
 
+// BatchNorm apply with the finalisation folded in (the last encoder layer materialises node_rep this way)
+__global__ void __launch_bounds__(256)
+k_bn_apply_fold(const float* __restrict__ x, int64_t ldx, int64_t M, int C, PgnnBnFold fold, int relu, float* __restrict__ y,
+                int64_t ldy) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float s_aff[];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) bn_fold_column(fold, C, c, blockIdx.x == 0, s_aff[c], s_aff[C + c]);
+  __syncthreads();
+  const int64_t total = M * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C;
+    const int c = (int)(idx - r * C);
+    float v = fmaf(x[r * ldx + c], s_aff[c], s_aff[C + c]);
+    if (relu) v = fmaxf(v, 0.f);
+    y[r * ldy + c] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_bn_eval(const float* __restrict__ x, int64_t ldx, int64_t M, int C, const float* __restrict__ gamma,
           const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps, int relu,
@@ -159,8 +177,8 @@ k_bn_bwd_apply(const float* __restrict__ gy, int64_t ldgy, const float* __restri
 __global__ void __launch_bounds__(256)
 k_bn_bwd_apply_colsum(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                      const float* __restrict__ invstd, int relu, const float* __restrict__ c1, const float* __restrict__ c2,
-                      float* __restrict__ gx, int64_t ldgx, float* __restrict__ colsum) {
+                      const float* __restrict__ invstd, int relu, const double* __restrict__ sums, float* __restrict__ ggamma,
+                      float* __restrict__ gbeta, float* __restrict__ gx, int64_t ldgx, float* __restrict__ colsum) {
   pdl_prologue();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -168,7 +186,13 @@ k_bn_bwd_apply_colsum(const float* __restrict__ gy, int64_t ldgy, const float* _
   const int r0 = blockIdx.y * kStatRows, r1 = min(M, r0 + kStatRows);
   float acc = 0.f;
   if (c < C) {
-    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c], k1 = c1[c], k2 = c2[c];
+    // finalisation of the statistics pass folded in: sum(dy), sum(dy*xhat) -> the two BatchNorm-backward means
+    const double sd = sums[c], sdx = sums[(int64_t)C + c];
+    if (blockIdx.y == 0 && w == 0) {
+      if (gbeta) gbeta[c] = (float)sd;
+      if (ggamma) ggamma[c] = (float)sdx;
+    }
+    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c], k1 = (float)(sd / M), k2 = (float)(sdx / M);
 #pragma unroll 4
     for (int r = r0 + w; r < r1; r += 8) {
       const float xhat = (x[(int64_t)r * ldx + c] - mu) * is;
@@ -256,17 +280,10 @@ inline int grid_items(int64_t items, int threads) {
 
 // encoder.cu: BatchNorm forward when the column sums / sums of squares were already accumulated (fp64, [2][C]) by the
 // epilogue of the GEMM that produced x (PgnnGemmHooks::stats)
-int pgnn_internal_bn_fwd_from_stats(const double* acc, const float* x, int64_t ldx, int64_t M, int64_t C, const float* gamma,
-                                    const float* beta, float* running_mean, float* running_var, int64_t* nbt, float momentum,
-                                    float eps, int relu, float* y, int64_t ldy, float* save_mean, float* save_invstd, float* scale,
-                                    float* shift, cudaStream_t st) {
-  PGNN_CUDA(pgnn_launch(k_bn_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, gamma, beta, running_mean, running_var, nbt,
-                                                           momentum, eps, save_mean, save_invstd, scale, shift));
+int pgnn_internal_bn_apply_fold(const float* x, int64_t ldx, int64_t M, int64_t C, const PgnnBnFold& fold, int relu, float* y,
+                                int64_t ldy, cudaStream_t st) {
+  PGNN_CUDA(pgnn_launch(k_bn_apply_fold, dim3(grid_items(M * C, 256)), dim3(256), sizeof(float) * 2 * C, st, x, ldx, M, (int)C, fold, relu, y, ldy));
   PGNN_LAUNCH_CHECK();
-  if (y) {
-    PGNN_CUDA(pgnn_launch(k_bn_apply, dim3(grid_items(M * C, 256)), dim3(256), 0, st, x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy));
-    PGNN_LAUNCH_CHECK();
-  }
   return PGNN_OK;
 }
 
@@ -282,10 +299,8 @@ int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, i
   dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
   PGNN_CUDA(pgnn_launch(k_bn_bwd_stats, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
   PGNN_LAUNCH_CHECK();
-  PGNN_CUDA(pgnn_launch(k_bn_bwd_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, ggamma, gbeta, c1, c2));
-  PGNN_LAUNCH_CHECK();
-  PGNN_CUDA(pgnn_launch(k_bn_bwd_apply_colsum, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, c1, c2, gx,
-                                            ldgx, colsum));
+  PGNN_CUDA(pgnn_launch(k_bn_bwd_apply_colsum, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu,
+                        (const double*)acc, ggamma, gbeta, gx, ldgx, colsum));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
