@@ -239,8 +239,8 @@ def run_b200(args, rank, world, local_rank):
         for p in params:
             p.grad = None
         rep = model(b["x"], b["edge_index"], b["edge_attr"])
-        logits = ops.linear(ops.row_gather(rep, b["masked_atom_indices"]), head.weight, head.bias)
-        loss = torch.nn.functional.cross_entropy(logits.double(), b["labels"])  # fp64 CE as the reference (:52)
+        # linear_pred_atoms(node_rep[masked_atom_indices]) + CrossEntropyLoss on .double() logits (reference :51-52)
+        loss, _ = ops.masked_atom_loss(rep, b["masked_atom_indices"], b["labels"], head.weight, head.bias)
         loss.backward()
         if reducer is not None:
             reducer.all_reduce_mean()

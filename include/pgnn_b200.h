@@ -215,6 +215,11 @@ PGNN_API int pgnn_row_gather_fwd(const float* x, int64_t ldx, const int64_t* idx
 /* gx[idx[m],:] += g[m,:] (and idx2). gx must be pre-initialised by the caller (accumulates). */
 PGNN_API int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const int64_t* idx2,
                                  int64_t num_idx, int64_t C, float* gx, int64_t ldgx, void* stream);
+/* Mean cross-entropy of fp32 logits [M,V] evaluated in fp64 (criterion(pred.double(), labels), chem/pretrain_masking.py:52).
+ * *loss_mean (device fp64 scalar) is OVERWRITTEN; dlogits [M, lddl] receives (softmax - onehot)/M (columns V..lddl-1 zeroed),
+ * i.e. the gradient of the loss w.r.t. the logits.  labels: int64 [M] in [0, V). */
+PGNN_API int pgnn_softmax_ce_fwd(const float* logits, int64_t ld, int64_t M, int64_t V, const int64_t* labels,
+                                 double* loss_mean, float* dlogits, int64_t lddl, void* stream);
 /* out[r] = sum_d a[r,d] * b[(r + shift) mod B, d]   (cycle_index negatives, pretrain_contextpred.py:36-39,64-67) */
 PGNN_API int pgnn_shifted_rowdot_fwd(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t B, int64_t C,
                                      int64_t shift, float* out, void* stream);

@@ -400,12 +400,13 @@ int pgnn_tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float*
 // gx[M,K] = (gy[M,N] . w[N,K]) masked by relu_src > 0
 int pgnn_tc_linear_bwd_x(const float* gy, int64_t ldgy, const float* w, int64_t M, int64_t N, int64_t K, const float* relu_src,
                          int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks) {
-  if (N % 4 || K % 4 || ldgy % 4 || !aligned16(gy) || !aligned16(w) || !aligned16(gx) || M < 1) return PGNN_EUNSUPPORTED;
+  if (K % 4 || ldgy % 4 || !aligned16(gy) || !aligned16(w) || !aligned16(gx) || M < 1) return PGNN_EUNSUPPORTED;
   TcEpilogue ep{nullptr, 0, relu_src, ldr, 0, hooks ? *hooks : PgnnGemmHooks{}};
   if (tma_enabled()) {  // A reduction-contiguous, B = w row-index-contiguous (MN-major boxes)
     const int rc = pgnn_tma_gemm(false, true, pick_bn((int)M, (int)K, 1), gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, 1, (int)N, ep, st);
     if (rc != PGNN_EUNSUPPORTED) return rc;
   }
+  if (N % 4) return PGNN_EUNSUPPORTED;  // the cp.async kernel moves 16-byte pieces along the reduction; TMA zero-fills ragged extents
   // output columns are K; the reduction runs over N; B(n_out = k, r = n) = w[r*K + k] is row-index contiguous
   return dispatch<true, false>(pick_bn((int)M, (int)K, 1), gy, ldgy, w, K, gx, ldgx, (int)M, (int)K, (int)N, 1, (int)N, ep, st);
 }
@@ -486,7 +487,8 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
 
 int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st) {
-  if (N % 4 || K % 4 || ldgy % 4 || ldx % 4 || !aligned16(gy) || !aligned16(x) || !aligned16(gw) || M < 1) return PGNN_EUNSUPPORTED;
+  if (K % 4 || ldgy % 4 || ldx % 4 || !aligned16(gy) || !aligned16(x) || !aligned16(gw) || M < 1) return PGNN_EUNSUPPORTED;
+  if ((N % 4) && !tma_enabled()) return PGNN_EUNSUPPORTED;  // ragged N (e.g. 119 classes) only through the TMA boxes
   // output [N, K] (rows N = "M" of the MMA), reduction over the M node rows, split so the grid fills the chip
   int bn = 224;  // the reduction is long and both operands are re-read per tile: widest tile with <= 15% padding
   for (int c : {224, 160, 128, 64}) {
@@ -521,7 +523,9 @@ int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64
     if (splits > 1) PGNN_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * N * K, st));
     TcEpilogue ep{nullptr, 0, nullptr, 0, splits > 1, PgnnGemmHooks{}};
     if (tma_enabled()) rc = pgnn_tma_gemm(true, true, bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
-    if (rc == PGNN_EUNSUPPORTED) rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+    if (rc == PGNN_EUNSUPPORTED && (N % 4) == 0)
+      rc = dispatch<false, false>(bn, gy, ldgy, x, ldx, gw, K, (int)N, (int)K, (int)M, splits, per, ep, st);
+    if (rc == PGNN_EUNSUPPORTED) return rc;
   }
   if (rc != PGNN_OK) return rc;
   if (gb) {

@@ -115,6 +115,36 @@ k_shifted_rowdot_bwd(const float* __restrict__ g, const float* __restrict__ a, i
   }
 }
 
+// Mean cross-entropy over fp32 logits evaluated in fp64, as `criterion(pred_node.double(), labels)` does
+// (chem/pretrain_masking.py:26,52).  One warp per row: max, log-sum-exp, -log p[label]; the same pass writes
+// dlogits = (softmax - onehot) / M, so the backward of the loss needs no kernel of its own.
+__global__ void __launch_bounds__(256)
+k_softmax_ce(const float* __restrict__ logits, int64_t ld, int64_t M, int V, const int64_t* __restrict__ labels,
+             double* __restrict__ loss_mean, float* __restrict__ dlogits, int64_t lddl) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const float* row = logits + r * ld;
+    double mx = -1e300;
+    for (int v = lane; v < V; v += 32) mx = fmax(mx, (double)row[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double se = 0.0;
+    for (int v = lane; v < V; v += 32) se += exp((double)row[v] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const double lse = mx + log(se);
+    const int64_t y = labels[r];
+    const double inv_m = 1.0 / (double)M;
+    for (int v = lane; v < V; v += 32) {
+      const double p = exp((double)row[v] - lse);
+      dlogits[r * lddl + v] = (float)((p - (v == y ? 1.0 : 0.0)) * inv_m);
+    }
+    for (int v = V + lane; v < lddl; v += 32) dlogits[r * lddl + v] = 0.f;  // padding columns of the 16-byte-aligned row
+    if (lane == 0) atomicAdd(loss_mean, (lse - (double)row[y]) * inv_m);
+  }
+}
+
 inline int grid_items(int64_t items, int threads) {
   int64_t b = ceil_div(items, threads);
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -172,6 +202,18 @@ int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const i
   if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
   PGNN_CUDA(pgnn_launch(k_row_gather_bwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), g, ldg, idx, idx2, num_idx, C4, gx, ldgx));
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+int pgnn_softmax_ce_fwd(const float* logits, int64_t ld, int64_t M, int64_t V, const int64_t* labels, double* loss_mean,
+                        float* dlogits, int64_t lddl, void* stream) {
+  PGNN_CHECK_ARG(M >= 0 && V > 0 && loss_mean && lddl >= V && ld >= V);
+  cudaStream_t st = as_stream(stream);
+  PGNN_CUDA(cudaMemsetAsync(loss_mean, 0, sizeof(double), st));
+  if (M == 0) return PGNN_OK;
+  PGNN_CHECK_ARG(logits && labels && dlogits);
+  PGNN_CUDA(pgnn_launch(k_softmax_ce, dim3(grid_items(M * 32, 256)), dim3(256), 0, st, logits, ld, M, (int)V, labels, loss_mean, dlogits, lddl));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -640,3 +640,59 @@ class _ChemGinEncoder(Function):
 
 def chem_gin_encoder(plan: ChemGinPlan, x, edge_index, edge_attr, training: bool):
     return _ChemGinEncoder.apply(plan, x, edge_index, edge_attr, training, *plan.params)
+
+
+# ------------------------------------------------------------------------------------------------
+# masking head: node_rep[idx] -> Linear -> mean cross-entropy in fp64 (chem/pretrain_masking.py:51-52) as one op
+# ------------------------------------------------------------------------------------------------
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class _MaskedCE(Function):
+    @staticmethod
+    def forward(ctx, node_rep, idx, labels, weight, bias):
+        _dev(node_rep, idx, labels, weight, bias)
+        rep, w = _f32(node_rep), _f32(weight).contiguous()
+        idx, labels = idx.contiguous(), labels.contiguous()
+        if idx.dtype != torch.int64 or labels.dtype != torch.int64:
+            raise PgnnError("indices and labels must be int64")
+        M, D, V = idx.shape[0], rep.shape[1], w.shape[0]
+        ldv = _pad4(V)  # 16-byte aligned logit rows: the TMA boxes of the backward GEMMs zero-fill the ragged class extent
+        dev = rep.device
+        rows = torch.empty(M, D, dtype=torch.float32, device=dev)
+        check(lib.pgnn_row_gather_fwd(_p(rep), rep.stride(0), _p(idx), None, M, D, _p(rows), D, _st()), "row_gather_fwd")
+        logits = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        check(lib.pgnn_linear_fwd(_p(rows), D, _p(w), _p(bias), M, V, D, 0, _p(logits), ldv, _precision, _st()), "linear_fwd")
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        dlogits = torch.empty(M, ldv, dtype=torch.float32, device=dev)
+        check(lib.pgnn_softmax_ce_fwd(_p(logits), ldv, M, V, _p(labels), _p(loss), _p(dlogits), ldv, _st()), "softmax_ce_fwd")
+        ctx.save_for_backward(rows, dlogits, w, idx)
+        ctx.dims = (tuple(rep.shape), M, D, V, ldv, bias is not None)
+        ctx.logits = logits[:, :V]
+        ctx.mark_non_differentiable(ctx.logits)
+        return loss, ctx.logits
+
+    @staticmethod
+    def backward(ctx, g, _g_logits):
+        rows, dlogits, w, idx = ctx.saved_tensors
+        (n, D_), M, D, V, ldv, has_bias = ctx.dims
+        dev = rows.device
+        dl = dlogits * g.to(torch.float32)  # d loss / d logits scaled by the incoming gradient (a scalar, normally 1)
+        gw = torch.empty(V, D, dtype=torch.float32, device=dev)
+        gb = torch.empty(V, dtype=torch.float32, device=dev) if has_bias else None
+        check(lib.pgnn_linear_bwd_w(_p(dl), ldv, _p(rows), D, M, V, D, _p(gw), _p(gb), _precision, _st()), "linear_bwd_w")
+        grep = None
+        if ctx.needs_input_grad[0]:
+            drows = torch.empty(M, D, dtype=torch.float32, device=dev)
+            check(lib.pgnn_linear_bwd_x(_p(dl), ldv, _p(w), M, V, D, None, 0, _p(drows), D, _precision, _st()), "linear_bwd_x")
+            grep = torch.zeros(n, D, dtype=torch.float32, device=dev)
+            check(lib.pgnn_row_gather_bwd(_p(drows), D, _p(idx), None, M, D, _p(grep), D, _st()), "row_gather_bwd")
+        return grep, None, None, gw, gb
+
+
+def masked_atom_loss(node_rep, masked_atom_indices, labels, weight, bias=None):
+    """`criterion(linear(node_rep[masked_atom_indices]).double(), labels)` of chem/pretrain_masking.py:51-52 with
+    nn.CrossEntropyLoss (mean): gather, Linear(emb_dim, V), softmax cross-entropy evaluated in fp64.
+    Returns (loss: fp64 scalar tensor, logits: [M, V] fp32, non-differentiable — e.g. for compute_accuracy)."""
+    return _MaskedCE.apply(node_rep, masked_atom_indices, labels, weight, bias)

@@ -285,3 +285,22 @@ def test_config5_full_size_b256(t):
     model, out = _run("chem", t, b, P, True)
     out.square().mean().backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_masked_atom_loss_op_vs_oracle():
+    """ops.masked_atom_loss = gather + Linear(300,119) + fp64 mean CE (chem/pretrain_masking.py:51-52) in one op."""
+    b = syn.mask_atoms(syn.zinc_batch(64, 3), 3)
+    g = torch.Generator().manual_seed(4)
+    rep = torch.randn(b["x"].shape[0], 300, generator=g)
+    W, bias = torch.randn(119, 300, generator=g) * 0.05, torch.randn(119, generator=g) * 0.05
+    r32 = [t.clone().requires_grad_(True) for t in (rep, W, bias)]
+    loss_ref, logits_ref = O.masking_loss(r32[0], b["masked_atom_indices"], b["mask_node_label"][:, 0], r32[1], r32[2])
+    loss_ref.backward()
+    d = [t.clone().to(DEV).requires_grad_(True) for t in (rep, W, bias)]
+    loss, logits = ops.masked_atom_loss(d[0], b["masked_atom_indices"].to(DEV), b["mask_node_label"][:, 0].to(DEV), d[1], d[2])
+    loss.backward()
+    assert loss.dtype == torch.float64 and abs(loss.item() - loss_ref.item()) < 1e-6
+    assert torch.allclose(logits.cpu(), logits_ref.detach(), atol=1e-4, rtol=1e-4)
+    for mine, ref in zip(d, r32):
+        e = (mine.grad.cpu() - ref.grad).abs().max().item() / max(ref.grad.abs().max().item(), 1e-8)
+        assert e < 2e-4, e
