@@ -16,6 +16,7 @@
 //   epilogue (warps 0-7): tc_common.cuh, identical to dense_tc.cu (two accumulators, staged coalesced stores, hooks).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -45,6 +46,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 // K-major operand, SWIZZLE_128B (layout type 2): 8-row groups are 1024 B apart; LBO is unused for swizzled K-major
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -57,7 +78,11 @@ __device__ __forceinline__ uint64_t tma_desc(uint32_t base, int j) {
   return umma_desc_sw128(base + j * 32);                         // 8 fp32 = 32 B inside the 128 B swizzle row
 }
 
-template <bool A_MN, bool B_MN, int BN>
+// CL2: the grid is launched in clusters of two CTAs along y (two 128-row output tiles with the same column tile).  They need the
+// same B tile, so each CTA fetches HALF of it and TMA-multicasts it into both CTAs' shared memory: operand bytes pulled per
+// CTA and block drop from A + B to A + B/2 (the main loop is bound by L2->SM operand traffic).  A raw stage may only be
+// refilled when BOTH CTAs have consumed it, hence raw_empty counts two arrivals, delivered by a multicast tcgen05.commit.
+template <bool A_MN, bool B_MN, int BN, bool CL2>
 __global__ void __launch_bounds__(T_NTHREADS, 1)
 k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
                   int64_t ldc, int M, int N, int K, int k_per_split, TcEpilogue ep) {
@@ -88,7 +113,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (threadIdx.x == 32) {
     for (int s = 0; s < NRAW; ++s) {
       mbar_init(smem_u32(&raw_full[s]), 1);
-      mbar_init(smem_u32(&raw_empty[s]), 1);
+      mbar_init(smem_u32(&raw_empty[s]), CL2 ? 2 : 1);
     }
     for (int s = 0; s < T_NLO; ++s) {
       mbar_init(smem_u32(&lo_full[s]), NPRODUCER / 32);
@@ -100,6 +125,8 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
+  if (CL2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   const uint32_t tmem_acc = tmem_base_s;
   constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
   // everything above (TMEM allocation, barrier init) is independent of the previous kernel's output
@@ -126,7 +153,15 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         } else {
           tma_load_2d(da, &tmap_a, bar, k0, m0);
         }
-        if (B_MN) {
+        if (CL2) {  // this CTA's half of the B tile, delivered to both CTAs of the pair
+          if (B_MN) {
+#pragma unroll
+            for (int b = 0; b < BN / 32; ++b)
+              if ((b & 1) == (int)crank) tma_load_2d_mc(db + b * MNB_BYTES, &tmap_b, bar, n0 + 32 * b, k0, (uint16_t)3);
+          } else {
+            tma_load_2d_mc(db + crank * (BN / 2) * 128, &tmap_b, bar, k0, n0 + crank * (BN / 2), (uint16_t)3);
+          }
+        } else if (B_MN) {
 #pragma unroll
           for (int b = 0; b < BN / 32; ++b) tma_load_2d(db + b * MNB_BYTES, &tmap_b, bar, n0 + 32 * b, k0);
         } else {
@@ -153,7 +188,8 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           umma_tf32(tmem_acc, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bh, j), idesc, first);
         }
         umma_commit(smem_u32(&lo_empty[kb % T_NLO]));
-        umma_commit(smem_u32(&raw_empty[kb % NRAW]));
+        if (CL2) umma_commit_mc(smem_u32(&raw_empty[kb % NRAW]), (uint16_t)3);  // both CTAs of the pair learn that this one is done
+        else umma_commit(smem_u32(&raw_empty[kb % NRAW]));
         if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));
       }
       __syncwarp();
@@ -183,18 +219,16 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (warp == 0 && kb == nkb - 1) TC_TRACE(3);  // last block converted
     }
   }
-  if (warp >= NPRODUCER / 32) {
-    tc_fence_before();
-    __syncthreads();
-    return;
+  if (warp < NPRODUCER / 32) {
+    if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    if (warp == 0) TC_TRACE(6);
+    tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
+    if (warp == 0) TC_TRACE(7);
   }
-  if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
-  tc_fence_after();
-  if (warp == 0) TC_TRACE(6);
-  tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
-  if (warp == 0) TC_TRACE(7);
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();  // neither CTA leaves while the other may still multicast data or barrier arrivals at it
   if (warp == 0) TC_TRACE(8);
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
@@ -262,19 +296,41 @@ bool cached_map(CUtensorMap* out, const float* base, bool mn, int64_t R, int64_t
   return true;
 }
 
+// Opt-in (PGNN_CLUSTER=1).  Measured on B200 (tools/check_tc.py): numerically identical, but NOT faster — 30.7 vs 30.0 us for
+// GEMM1, 35.0 vs 30.5 us for GEMM2, and split-K wgrads lose a wave to the padding partner CTA.  The main loop is bound by
+// shared-memory bandwidth (TMA writes 44 KB + lo conversion 88 KB + tensor-core operand reads 132 KB per 32-deep block
+// at 128 B/clk = 1.07 us, measured 1.24 us), which multicast does not reduce; it only removes L2 traffic.
+bool cluster_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_CLUSTER");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <bool A_MN, bool B_MN, int BN>
 int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits,
                int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
+  const int mt = (int)ceil_div(M, BM);
+  const bool cl2 = cluster_enabled() && mt >= 2;  // pairs of row tiles share the column tile's B operand
   alignas(64) CUtensorMap ma, mb;
-  if (!cached_map(&ma, A, A_MN, M, K, lda, BM) || !cached_map(&mb, B, B_MN, N, K, ldb, BN)) return PGNN_EUNSUPPORTED;
+  if (!cached_map(&ma, A, A_MN, M, K, lda, BM) || !cached_map(&mb, B, B_MN, N, K, ldb, (cl2 && !B_MN) ? BN / 2 : BN)) return PGNN_EUNSUPPORTED;
   constexpr int smem = TmaCfg<BN>::SMEM;
   static bool configured = false;
   if (!configured) {
-    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
-  PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN>, dim3(grid), dim3(T_NTHREADS), smem, st, ma, mb, C, ldc, M, N, K, k_per_split, ep));
+  if (cl2) {
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)(mt + (mt & 1)), (unsigned)splits);  // an odd tile count gets an all-padding partner CTA
+    PGNN_CUDA(pgnn_launch_cluster_y(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, dim3(grid), dim3(T_NTHREADS), smem, st, 2u, ma, mb, C, ldc, M, N, K,
+                                    k_per_split, ep));
+  } else {
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)mt, (unsigned)splits);
+    PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, dim3(grid), dim3(T_NTHREADS), smem, st, ma, mb, C, ldc, M, N, K, k_per_split, ep));
+  }
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
