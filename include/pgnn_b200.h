@@ -255,6 +255,41 @@ PGNN_API int pgnn_chem_gin_backward(const void* const* params, const float* g_no
                                     int64_t N, int64_t E, int64_t L, int64_t D, int precision, float* grads,
                                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Either side of the path inside a training step (f1 collation, f2 optimizer).
+ * ------------------------------------------------------------------------------------------- */
+/* Device-side batch collation for chem graphs: what BatchMasking.from_data_list / BatchSubstructContext do on the host
+ * (chem/batch.py:17-52: concatenate per-graph tensors, add the running node count to edge_index, build `batch`).
+ * The molecule store is resident in HBM in compact form:
+ *   node_ptr[G+1], edge_ptr[G+1]  int64 prefix sums of atoms / directed bonds per graph
+ *   store_x[2*Nt] uint8 (atom type, chirality), store_edge_attr[2*Et] uint8 (bond type, direction), both row-major [.,2]
+ *   store_edge_index[2][Et] int32, graph-LOCAL endpoints (row 0 then row 1, as edge_index)
+ * graph_ids[B] int64 selects and orders the graphs of the batch.  Outputs (sizes N = sum n_g, E = sum e_g, which the host
+ * knows from its copy of the prefix sums): x [N,2], edge_index [2,E], edge_attr [E,2], batch [N], all int64 as GNN.forward
+ * takes them; node_off / edge_off [B+1] int64 receive the exclusive scans (node_off is the per-graph offset the reference
+ * adds to masked_atom_indices, chem/batch.py:40-45).  Bit-exact. */
+PGNN_API int pgnn_collate_chem(const int64_t* node_ptr, const int64_t* edge_ptr, const uint8_t* store_x,
+                               const int32_t* store_edge_index, int64_t store_num_edges, const uint8_t* store_edge_attr,
+                               const int64_t* graph_ids, int64_t B, int64_t* node_off, int64_t* edge_off, int64_t* x,
+                               int64_t* edge_index, int64_t* edge_attr, int64_t* batch, void* stream);
+
+/* Multi-tensor Adam: torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.decay).step()
+ * (chem/pretrain_masking.py:134-136,72-74; chem/pretrain_contextpred.py:160-161,96-97) for every tensor in one launch.
+ * `chunks` is a DEVICE array; each chunk is a contiguous run of at most a few thousand elements of one tensor
+ * (one CTA per chunk).  grad is read as grad*grad_scale (1/world_size folds the data-parallel mean in) and is not
+ * modified.  Hyper-parameters are doubles (Python floats): 1-beta and the bias corrections are formed in double on the
+ * host and rounded to fp32 once, as torch does.  step >= 1 is the 1-based step count.  legacy_eps = 0: current torch (denom = sqrt(v)/sqrt(bc2) + eps);
+ * legacy_eps = 1: torch 1.0.1 as pinned by the reference (denom = sqrt(v) + eps, step = lr*sqrt(bc2)/bc1). */
+typedef struct PgnnAdamChunk {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} PgnnAdamChunk;
+PGNN_API int pgnn_adam_step(const PgnnAdamChunk* chunks, int64_t num_chunks, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, double grad_scale, int64_t step, int legacy_eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

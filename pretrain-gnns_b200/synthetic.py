@@ -155,3 +155,13 @@ def ppi_batch(num_graphs: int, seed: int, n_lo: int = 400, n_hi: int = 600, pair
                 edge_attr=_t(np.concatenate(eas), torch.float32), batch=_t(np.concatenate(bs)),
                 center_node_idx=_t(ptr[:-1]), ptr=_t(ptr), go_target_pretrain=_t(y.reshape(-1)),
                 num_graphs=num_graphs)
+
+
+def split_graphs(batch: dict):
+    """Per-graph (x [n,2], edge_index [2,e] graph-LOCAL, edge_attr [e,2]) numpy arrays of a zinc_batch: the form a dataset
+    holds before collation (chem/loader.py:53-100 builds one such Data per molecule)."""
+    ptr = batch["ptr"].numpy()
+    x, ei, ea = batch["x"].numpy(), batch["edge_index"].numpy(), batch["edge_attr"].numpy()
+    owner = np.searchsorted(ptr, ei[0], side="right") - 1  # edges are emitted graph by graph
+    eptr = np.searchsorted(owner, np.arange(len(ptr)))
+    return [(x[ptr[g]:ptr[g + 1]], ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]]) for g in range(len(ptr) - 1)]
