@@ -111,9 +111,10 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_trigger();
 }
 
-// same, for thread-block clusters of `cluster` CTAs along grid.y
+// same, for thread-block clusters of `cluster` CTAs along grid.x (kernels that use tcgen05 cta_group::2 are rejected with
+// cudaErrorInvalidClusterSize unless the pair lies along x)
 template <typename... KArgs, typename... Args>
-inline cudaError_t pgnn_launch_cluster_y(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster,
+inline cudaError_t pgnn_launch_cluster_x(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster,
                                          Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -124,8 +125,8 @@ inline cudaError_t pgnn_launch_cluster_y(void (*kernel)(KArgs...), dim3 grid, di
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   attr[1].id = cudaLaunchAttributeClusterDimension;
-  attr[1].val.clusterDim.x = 1;
-  attr[1].val.clusterDim.y = cluster;
+  attr[1].val.clusterDim.x = cluster;
+  attr[1].val.clusterDim.y = 1;
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;

@@ -14,6 +14,14 @@
 //   warp 8   MMA issuer: wait lo_full[t] -> fence.proxy.async -> 4 k-steps x 3 tcgen05.mma (raw tile = hi operand,
 //            SWIZZLE_128B K-major descriptors, start address advanced 32 B per k-step) -> commit lo_empty[t], raw_empty[s]
 //   epilogue (warps 0-7): tc_common.cuh, identical to dense_tc.cu (two accumulators, staged coalesced stores, hooks).
+//
+// PAIR variant (K-major operands, no split-K): the grid is launched in clusters of two CTAs along x (row tiles) and the pair runs
+// tcgen05.mma.cta_group::2 with M = 256: each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the
+// leader CTA (rank 0) issues every MMA, and each CTA's TMEM receives the accumulator rows of its own 128-row tile.  The
+// main loop is bound by shared-memory bandwidth (TMA writes + lo conversion + 3x operand reads); halving the B bytes per
+// SM takes 264 KB per 32-deep block down to 180 KB at BN = 224.  Protocol differences: the converters of BOTH CTAs
+// arrive on the LEADER's lo_full (remote mbarrier arrive, release.cluster, after a generic->async proxy fence), and the
+// leader's commits are multicast to both CTAs' lo_empty / raw_empty / acc_bar.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -26,15 +34,22 @@ namespace {
 
 constexpr int TBK = 32;                         // fp32 per reduction block = one 128-byte swizzle row
 constexpr int T_NTHREADS = NPRODUCER + 64;      // 8 converter/epilogue warps + MMA warp + TMA warp
-constexpr int T_NLO = 2;
 
-template <int BN>
+template <int BN, bool PAIR>
 struct TmaCfg {
   static constexpr int A_BYTES = BM * TBK * 4;  // 16 KiB (either major: R rows x 32 k x 4 B)
-  static constexpr int B_BYTES = BN * TBK * 4;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TBK * 4;  // per CTA
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int NRAW = (STAGE <= 32768) ? 3 : 2;
-  static constexpr int SMEM = (NRAW + T_NLO) * STAGE + 1024;
+  // Ring depths.  The main loop is a latency chain, not a bandwidth limit: a raw stage is refilled only after the MMAs that read
+  // it complete (commit -> TMA issue -> TMA latency -> conversion -> arrive -> MMA: ~2.5 us), a lo stage likewise (~1.7 us), so
+  // a block costs max(tensor time, 2.5 us / NRAW, 1.7 us / NLO).  Measured at BN = 224: 1.22 us per block with 2 + 2 stages
+  // against 0.70 us of tensor time.  As many stages as 220 KiB hold, at most 4 + 4.
+  static constexpr int TOTAL = 225280 / STAGE;
+  static constexpr int NLO = TOTAL >= 8 ? 4 : TOTAL >= 6 ? 3 : 2;
+  static constexpr int NRAW = (TOTAL - NLO) < 4 ? (TOTAL - NLO) : 4;
+  static constexpr int EPI = BM * (BN + 4) * 4 + BM * 16 * 4;  // epilogue staging tile + the hooks' [128][Q <= 16] slice
+  static constexpr int RING = (NRAW + NLO) * STAGE;
+  static constexpr int SMEM = (RING > EPI ? RING : EPI) + 1024;
 };
 constexpr int MNB_BYTES = 32 * TBK * 4;  // one MN-major box: 32 k rows x 128 B
 
@@ -46,15 +61,47 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+// cta_group::2 forms: one MMA over the CTA pair (M = 256), commit delivered to the same barrier offset in both CTAs
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
                : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+// mbar_wait with cluster-scope acquire (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint64_t t0 = globaltimer_ns();
+#pragma unroll 1
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u && globaltimer_ns() - t0 > 2000000000ull) break;
+  }
+  asm volatile("trap;");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -78,16 +125,13 @@ __device__ __forceinline__ uint64_t tma_desc(uint32_t base, int j) {
   return umma_desc_sw128(base + j * 32);                         // 8 fp32 = 32 B inside the 128 B swizzle row
 }
 
-// CL2: the grid is launched in clusters of two CTAs along y (two 128-row output tiles with the same column tile).  They need the
-// same B tile, so each CTA fetches HALF of it and TMA-multicasts it into both CTAs' shared memory: operand bytes pulled per
-// CTA and block drop from A + B to A + B/2 (the main loop is bound by L2->SM operand traffic).  A raw stage may only be
-// refilled when BOTH CTAs have consumed it, hence raw_empty counts two arrivals, delivered by a multicast tcgen05.commit.
-template <bool A_MN, bool B_MN, int BN, bool CL2>
+template <bool A_MN, bool B_MN, int BN, bool PAIR>
 __global__ void __launch_bounds__(T_NTHREADS, 1)
 k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
                   int64_t ldc, int M, int N, int K, int k_per_split, TcEpilogue ep) {
-  using Cfg = TmaCfg<BN>;
-  constexpr int NRAW = Cfg::NRAW;
+  static_assert(!PAIR || (!A_MN && !B_MN && BN % 32 == 0), "the pair variant takes K-major operands; UMMA N % 16 == 0 at M = 256");
+  using Cfg = TmaCfg<BN, PAIR>;
+  constexpr int NRAW = Cfg::NRAW, T_NLO = Cfg::NLO;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], lo_full[T_NLO], lo_empty[T_NLO], acc_bar;
   __shared__ uint32_t tmem_base_s;
@@ -97,26 +141,34 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   auto lo = [&](int kb) { return smem + (NRAW + kb % T_NLO) * Cfg::STAGE; };     // [A lo | B lo]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // pair: the two row tiles of a pair are neighbours along grid.x (the cluster dimension cta_group::2 kernels must use)
+  const int m0 = (PAIR ? blockIdx.x : blockIdx.y) * BM, n0 = (PAIR ? blockIdx.y : blockIdx.x) * BN;
   const int kbeg = blockIdx.z * k_per_split;  // k_per_split % 32 == 0 whenever there is more than one split
   const int kend = min(K, kbeg + k_per_split);
   const int nkb = (kend - kbeg + TBK - 1) / TBK;
   const bool s_bias_on = ep.bias != nullptr && blockIdx.z == 0;
   if (warp == 0) TC_TRACE(0);
 
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"((uint32_t)tmem_cols<BN>())
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 0) {  // pair: warp 0 of BOTH CTAs, same destination offset
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                   "r"((uint32_t)tmem_cols<BN>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                   "r"((uint32_t)tmem_cols<BN>())
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (threadIdx.x == 32) {
     for (int s = 0; s < NRAW; ++s) {
       mbar_init(smem_u32(&raw_full[s]), 1);
-      mbar_init(smem_u32(&raw_empty[s]), CL2 ? 2 : 1);
+      mbar_init(smem_u32(&raw_empty[s]), 1);
     }
     for (int s = 0; s < T_NLO; ++s) {
-      mbar_init(smem_u32(&lo_full[s]), NPRODUCER / 32);
+      mbar_init(smem_u32(&lo_full[s]), (PAIR ? 2 : 1) * (NPRODUCER / 32));  // pair: the leader's copy collects both CTAs' converters
       mbar_init(smem_u32(&lo_empty[s]), 1);
     }
     mbar_init(smem_u32(&acc_bar), 1);
@@ -125,10 +177,10 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
-  if (CL2) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything arrives at them
   const uint32_t tmem_acc = tmem_base_s;
-  constexpr uint32_t idesc = umma_idesc(BM, BN, A_MN, B_MN);
+  constexpr uint32_t idesc = umma_idesc(PAIR ? 2 * BM : BM, BN, A_MN, B_MN);
   // everything above (TMEM allocation, barrier init) is independent of the previous kernel's output
   pdl_prologue();
   if (threadIdx.x < NPRODUCER)
@@ -153,14 +205,8 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         } else {
           tma_load_2d(da, &tmap_a, bar, k0, m0);
         }
-        if (CL2) {  // this CTA's half of the B tile, delivered to both CTAs of the pair
-          if (B_MN) {
-#pragma unroll
-            for (int b = 0; b < BN / 32; ++b)
-              if ((b & 1) == (int)crank) tma_load_2d_mc(db + b * MNB_BYTES, &tmap_b, bar, n0 + 32 * b, k0, (uint16_t)3);
-          } else {
-            tma_load_2d_mc(db + crank * (BN / 2) * 128, &tmap_b, bar, k0, n0 + crank * (BN / 2), (uint16_t)3);
-          }
+        if (PAIR) {  // this CTA's half of the column tile (the tensor map's box is BN/2 rows)
+          tma_load_2d(db, &tmap_b, bar, k0, n0 + (int)crank * (BN / 2));
         } else if (B_MN) {
 #pragma unroll
           for (int b = 0; b < BN / 32; ++b) tma_load_2d(db + b * MNB_BYTES, &tmap_b, bar, n0 + 32 * b, k0);
@@ -170,29 +216,43 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp == 8) {
-    // ---------------- MMA issuer ----------------
+    // ---------------- MMA issuer (pair: the leader CTA only) ----------------
+    if (!PAIR || crank == 0) {
 #pragma unroll 1
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(smem_u32(&lo_full[kb % T_NLO]), (kb / T_NLO) & 1);
-      fence_async_smem();  // the converters' generic-proxy lo stores, observed through the barrier -> async proxy
-      tc_fence_after();
-      if (kb == 0) TC_TRACE(4);
-      if (kb == nkb - 1) TC_TRACE(5);
-      if (lane == 0) {
-        const uint32_t ah = smem_u32(raw(kb)), bh = ah + Cfg::A_BYTES, al = smem_u32(lo(kb)), bl = al + Cfg::A_BYTES;
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (PAIR) mbar_wait_cluster(smem_u32(&lo_full[kb % T_NLO]), (kb / T_NLO) & 1);
+        else mbar_wait(smem_u32(&lo_full[kb % T_NLO]), (kb / T_NLO) & 1);
+        fence_async_smem();  // the converters' generic-proxy lo stores, observed through the barrier -> async proxy
+        tc_fence_after();
+        if (kb == 0) TC_TRACE(4);
+        if (kb == nkb - 1) TC_TRACE(5);
+        if (lane == 0) {
+          const uint32_t ah = smem_u32(raw(kb)), bh = ah + Cfg::A_BYTES, al = smem_u32(lo(kb)), bl = al + Cfg::A_BYTES;
 #pragma unroll
-        for (int j = 0; j < TBK / 8; ++j) {
-          const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
-          umma_tf32(tmem_acc + BN, tma_desc<A_MN>(al, j), tma_desc<B_MN>(bh, j), idesc, first);  // cross terms
-          umma_tf32(tmem_acc + BN, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bl, j), idesc, 1u);
-          umma_tf32(tmem_acc, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bh, j), idesc, first);
+          for (int j = 0; j < TBK / 8; ++j) {
+            const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
+            if (PAIR) {
+              umma_tf32_pair(tmem_acc + BN, tma_desc<A_MN>(al, j), tma_desc<B_MN>(bh, j), idesc, first);  // cross terms
+              umma_tf32_pair(tmem_acc + BN, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bl, j), idesc, 1u);
+              umma_tf32_pair(tmem_acc, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bh, j), idesc, first);
+            } else {
+              umma_tf32(tmem_acc + BN, tma_desc<A_MN>(al, j), tma_desc<B_MN>(bh, j), idesc, first);  // cross terms
+              umma_tf32(tmem_acc + BN, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bl, j), idesc, 1u);
+              umma_tf32(tmem_acc, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bh, j), idesc, first);
+            }
+          }
+          if (PAIR) {  // both CTAs' stages were read by these MMAs: release them in both
+            umma_commit_pair(smem_u32(&lo_empty[kb % T_NLO]));
+            umma_commit_pair(smem_u32(&raw_empty[kb % NRAW]));
+            if (kb == nkb - 1) umma_commit_pair(smem_u32(&acc_bar));
+          } else {
+            umma_commit(smem_u32(&lo_empty[kb % T_NLO]));
+            umma_commit(smem_u32(&raw_empty[kb % NRAW]));
+            if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));
+          }
         }
-        umma_commit(smem_u32(&lo_empty[kb % T_NLO]));
-        if (CL2) umma_commit_mc(smem_u32(&raw_empty[kb % NRAW]), (uint16_t)3);  // both CTAs of the pair learn that this one is done
-        else umma_commit(smem_u32(&raw_empty[kb % NRAW]));
-        if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ---------------- converters ----------------
@@ -213,8 +273,12 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
         dst[i] = l;
       }
+      if (PAIR) fence_async_smem();  // writer-side proxy fence: the peer CTA's tensor-core reads are ordered through a remote arrive
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&lo_full[kb % T_NLO]));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(smem_u32(&lo_full[kb % T_NLO]), 0u);
+        else mbar_arrive(smem_u32(&lo_full[kb % T_NLO]));
+      }
       if (warp == 0 && kb == 0) TC_TRACE(2);        // first block converted
       if (warp == 0 && kb == nkb - 1) TC_TRACE(3);  // last block converted
     }
@@ -228,10 +292,11 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (CL2) cluster_sync_all();  // neither CTA leaves while the other may still multicast data or barrier arrivals at it
+  if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees its TMEM half) while the pair's MMAs or barrier arrivals may still target it
   if (warp == 0) TC_TRACE(8);
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
   }
 }
 
@@ -296,14 +361,17 @@ bool cached_map(CUtensorMap* out, const float* base, bool mn, int64_t R, int64_t
   return true;
 }
 
-// Opt-in (PGNN_CLUSTER=1).  Measured on B200 (tools/check_tc.py): numerically identical, but NOT faster — 30.7 vs 30.0 us for
-// GEMM1, 35.0 vs 30.5 us for GEMM2, and split-K wgrads lose a wave to the padding partner CTA.  The main loop is bound by
-// shared-memory bandwidth (TMA writes 44 KB + lo conversion 88 KB + tensor-core operand reads 132 KB per 32-deep block
-// at 128 B/clk = 1.07 us, measured 1.24 us), which multicast does not reduce; it only removes L2 traffic.
-bool cluster_enabled() {
+// CTA pairs (cta_group::2) for the K-major x K-major GEMMs: opt-in with PGNN_PAIR=1.  Measured on B200 (tools/check_tc.py,
+// tools/trace_tc.py): numerically identical to the single-CTA kernel, but a 32-deep block costs 1.05-1.08 us whatever the tile
+// width (BN = 224 and 128 alike, also for a lone cluster on an idle GPU, with or without the proxy fence / cluster-scope
+// wait), i.e. ~90 ns per UTCHMMA.2CTA with K = 8, against 1.05 us (BN 224) / 0.79 us (BN 128) for the single-CTA kernel with
+// the same ring depths.  GEMM1 31.0 vs 27.6 us, GEMM2 38.7 vs 29.2 us.  Kept as the starting point for a wider-K variant.
+// (An earlier 2-CTA variant that only TMA-multicast the B tile into both CTAs also measured no gain: at cluster size 2 the L2
+// already deduplicates the pair's requests.)
+bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("PGNN_CLUSTER");
+    const char* e = getenv("PGNN_PAIR");
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
@@ -312,25 +380,34 @@ bool cluster_enabled() {
 template <bool A_MN, bool B_MN, int BN>
 int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K, int splits,
                int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
-  const int mt = (int)ceil_div(M, BM);
-  const bool cl2 = cluster_enabled() && mt >= 2;  // pairs of row tiles share the column tile's B operand
+  const int mt = (int)ceil_div(M, BM), nt = (int)ceil_div(N, BN);
+  constexpr bool kPairable = !A_MN && !B_MN && (BN % 32 == 0);
+  // pairs of row tiles share the column tile; an odd tile count gets an all-padding partner, which must not cost a wave
+  const int64_t ctas = (int64_t)mt * nt, ctas_pair = (int64_t)(mt + (mt & 1)) * nt;
+  const bool pair = kPairable && pair_enabled() && splits == 1 && mt >= 2 && ceil_div(ctas_pair, kNumSMs) <= ceil_div(ctas, kNumSMs);
   alignas(64) CUtensorMap ma, mb;
-  if (!cached_map(&ma, A, A_MN, M, K, lda, BM) || !cached_map(&mb, B, B_MN, N, K, ldb, (cl2 && !B_MN) ? BN / 2 : BN)) return PGNN_EUNSUPPORTED;
-  constexpr int smem = TmaCfg<BN>::SMEM;
+  if (!cached_map(&ma, A, A_MN, M, K, lda, BM) || !cached_map(&mb, B, B_MN, N, K, ldb, pair ? BN / 2 : BN)) return PGNN_EUNSUPPORTED;
   static bool configured = false;
   if (!configured) {
-    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TmaCfg<BN, false>::SMEM));
+    if constexpr (kPairable)
+      PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TmaCfg<BN, true>::SMEM));
     configured = true;
   }
-  if (cl2) {
-    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)(mt + (mt & 1)), (unsigned)splits);  // an odd tile count gets an all-padding partner CTA
-    PGNN_CUDA(pgnn_launch_cluster_y(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, dim3(grid), dim3(T_NTHREADS), smem, st, 2u, ma, mb, C, ldc, M, N, K,
-                                    k_per_split, ep));
-  } else {
-    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)mt, (unsigned)splits);
-    PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, dim3(grid), dim3(T_NTHREADS), smem, st, ma, mb, C, ldc, M, N, K, k_per_split, ep));
+  if constexpr (kPairable) {
+    if (pair) {
+      dim3 grid((unsigned)(mt + (mt & 1)), (unsigned)nt, 1u);
+      PGNN_CUDA(pgnn_launch_cluster_x(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, dim3(grid), dim3(T_NTHREADS), TmaCfg<BN, true>::SMEM, st, 2u,
+                                      ma, mb, C, ldc, M, N, K, k_per_split, ep));
+      PGNN_LAUNCH_CHECK();
+      return PGNN_OK;
+    }
   }
+  dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
+  PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, dim3(grid), dim3(T_NTHREADS), TmaCfg<BN, false>::SMEM, st, ma, mb, C, ldc, M, N,
+                        K, k_per_split, ep));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

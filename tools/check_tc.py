@@ -64,7 +64,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "warm":
         COLD = False
         print("warm L2 (no flush between launches)")
-    for shape in [(5986, 600, 300), (5986, 300, 600), (130, 600, 300), (1, 8, 4), (1024, 119, 300), (32000, 600, 600), (777, 300, 300)]:
+    shapes = [(5986, 600, 300), (5986, 300, 600), (130, 600, 300), (1, 8, 4), (1024, 119, 300), (32000, 600, 600), (777, 300, 300)]
+    if 'quick' in sys.argv:
+        shapes = shapes[:2]
+    for shape in shapes:
         M, N, K = shape
         if N % 4:  # dgrad/wgrad of the tensor path need N % 4 == 0; the library falls back to FFMA there
             pass
