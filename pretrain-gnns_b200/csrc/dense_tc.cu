@@ -158,7 +158,7 @@ k_gemm_3xtf32(const float* __restrict__ A, int64_t lda, const float* __restrict_
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[NLO], raw_empty[NRAW], lo_empty[NLO], acc_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[BN];  // this tile's bias slice (zero past N), loaded once at the prologue
+  __shared__ __align__(16) float s_bias[BN];  // this tile's bias slice (zero past N), loaded once at the prologue
 
   uint8_t* bufs = smem;
   constexpr int STAGE_BYTES = OpA::BYTES + OpB::BYTES;
@@ -463,9 +463,18 @@ namespace {
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, int64_t n4, float* __restrict__ out) {
   pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 a = reinterpret_cast<const float4*>(part)[i];
-    for (int s = 1; s < splits; ++s) {
-      const float4 b = reinterpret_cast<const float4*>(part)[(int64_t)s * n4 + i];
+    const float4* p = reinterpret_cast<const float4*>(part) + i;
+    float4 a = p[0];
+    int s = 1;
+    for (; s + 3 < splits; s += 4) {  // four independent loads in flight; the sum order stays s = 0, 1, 2, ... (deterministic)
+      const float4 b0 = p[(int64_t)s * n4], b1 = p[(int64_t)(s + 1) * n4], b2 = p[(int64_t)(s + 2) * n4], b3 = p[(int64_t)(s + 3) * n4];
+      a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+      a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+      a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+      a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
+    }
+    for (; s < splits; ++s) {
+      const float4 b = p[(int64_t)s * n4];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     reinterpret_cast<float4*>(out)[i] = a;

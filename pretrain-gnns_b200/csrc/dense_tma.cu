@@ -135,7 +135,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], lo_full[T_NLO], lo_empty[T_NLO], acc_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_bias[BN];
 
   auto raw = [&](int kb) { return smem + (kb % NRAW) * Cfg::STAGE; };             // [A raw | B raw]
   auto lo = [&](int kb) { return smem + (NRAW + kb % T_NLO) * Cfg::STAGE; };     // [A lo | B lo]

@@ -193,9 +193,12 @@ __device__ __forceinline__ void tc_epilogue(uint8_t* smem, const float* s_bias, 
         if (!live[u]) continue;
         float ov[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
         const float mv[4] = {mk[u].x, mk[u].y, mk[u].z, mk[u].w};
+        // one 16-byte read: four scalar reads at a lane stride of 4 floats are 4-way bank conflicts each
+        const float4 b4 = s_bias_on ? *reinterpret_cast<const float4*>(s_bias + (gn[u] - n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (s_bias_on) ov[q] += s_bias[gn[u] - n0 + q];
+          if (s_bias_on) ov[q] += bv[q];
           if (ep.relu) ov[q] = fmaxf(ov[q], 0.f);
           ov[q] = mv[q] > 0.f ? ov[q] : 0.f;
         }
