@@ -295,6 +295,7 @@ def run_b200(args, rank, world, local_rank):
                    "nodes_per_batch": int(host[0]["x"].shape[0]), "edges_per_batch": int(host[0]["edge_index"].shape[1]),
                    "distinct_batches": NUM_DISTINCT_BATCHES, "l2": "flushed between timed steps (256 MiB memset)",
                    "optimizer_step": "excluded (SURVEY 8(d))", "gemm_precision": ops.get_precision(),
+                   "grad_allreduce": (reducer.backend if reducer is not None else "none (1 GPU)"),
                    "wall_ms_per_step_incl_flush": 1e3 * wall_dev / args.steps},
         "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps},

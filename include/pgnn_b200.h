@@ -290,6 +290,21 @@ typedef struct PgnnAdamChunk {
 PGNN_API int pgnn_adam_step(const PgnnAdamChunk* chunks, int64_t num_chunks, double lr, double beta1, double beta2, double eps,
                             double weight_decay, double grad_scale, int64_t step, int legacy_eps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory.  In place, two-shot (reduce-scatter by peer loads,
+ * all-gather by peer stores, three flag barriers), bit-identical on every rank, no library collective.
+ *   bufs  : DEVICE array of `world` pointers: the peer-mapped address of every rank's fp32 buffer of n elements (same offset
+ *           of a symmetric allocation on every rank; bufs[rank] is the local one)
+ *   flags : DEVICE array of `world` pointers to every rank's flag words (uint32[world], zero before the first call,
+ *           used by these calls only)
+ *   scratch: local device buffer of pgnn_allreduce_p2p_scratch_floats(n, world) floats
+ *   epoch : 0, 1, 2, ... incremented by the caller on every call, identical on all ranks
+ * On return (stream order) every rank's buffer holds scale * sum over ranks.  A rank that never arrives traps the waiting
+ * kernels after ~2 s (sticky CUDA error) instead of hanging. */
+PGNN_API int64_t pgnn_allreduce_p2p_scratch_floats(int64_t n, int world);
+PGNN_API int pgnn_allreduce_p2p(void* const* bufs, void* const* flags, int rank, int world, int64_t n, float scale,
+                                float* scratch, int64_t scratch_floats, int64_t epoch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

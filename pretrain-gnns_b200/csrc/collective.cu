@@ -1,0 +1,121 @@
+// Gradient all-reduce over NVLink peer memory (one all-reduce of the flat gradient buffer per step).
+//
+// The flat gradient buffer of every rank lives at the same offset of a symmetric allocation, so each rank holds the
+// peer-mapped address of every other rank's buffer and of a small flag array.  Two-shot, in place, no library collective:
+//
+//   barrier  (every rank's backward has finished and is visible)
+//   reduce-scatter: rank r sums slice r over all ranks' buffers (peer loads over NVLink, fixed rank order) -> local scratch
+//   barrier  (every rank has finished READING every buffer, so slices may be overwritten)
+//   all-gather: rank r stores its reduced slice into slice r of every rank's buffer (peer stores)
+//   barrier  (all stores have landed)
+//
+// Each element is summed by exactly one rank in the order 0..G-1, so all ranks end with bit-identical gradients and the
+// result does not depend on timing.  A cross-GPU barrier is a one-CTA kernel: thread t publishes a monotonically increasing
+// sequence number to rank t's flag word [rank] (st.release.sys after a system fence) and spins on its own flag word [t]
+// (ld.acquire.sys, time-bounded: a lost peer traps after ~2 s instead of hanging the GPU).  Kernel boundaries order the
+// phases inside a GPU.  For the 7.4 MB chem-GIN buffer on 2 GPUs this replaces a ~180 us NCCL call.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint64_t gtimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(32) k_xgpu_barrier(uint32_t* const* __restrict__ flags, int rank, int world, uint32_t seq) {
+  pdl_prologue();  // the previous kernel of this stream has completed and flushed
+  const int t = threadIdx.x;
+  if (t < world) {
+    __threadfence_system();
+    uint32_t* remote = flags[t] + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(seq) : "memory");
+    const uint32_t* mine = flags[rank] + t;
+    const uint64_t t0 = gtimer_ns();
+    for (uint32_t it = 0;; ++it) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - seq) >= 0) break;
+      if ((it & 255u) == 255u && gtimer_ns() - t0 > 2000000000ull) asm volatile("trap;");
+    }
+  }
+}
+
+__device__ __forceinline__ float4 ld_peer4(const float* p) { return __ldcv(reinterpret_cast<const float4*>(p)); }
+
+// scratch[i - lo] = scale * sum_k bufs[k][i] for i in [lo, hi)
+__global__ void __launch_bounds__(256)
+k_reduce_slice(float* const* __restrict__ bufs, int world, int64_t lo, int64_t hi, float scale, float* __restrict__ scratch) {
+  pdl_prologue();
+  const int64_t n = hi - lo;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(bufs[0] + lo) & 15) == 0) ? n / 4 : 0;  // symmetric offsets: same alignment on every rank
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = ld_peer4(bufs[0] + lo + 4 * i);
+    for (int k = 1; k < world; ++k) {
+      const float4 b = ld_peer4(bufs[k] + lo + 4 * i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(scratch)[i] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+  }
+  for (int64_t i = 4 * n4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float a = __ldcv(bufs[0] + lo + i);
+    for (int k = 1; k < world; ++k) a += __ldcv(bufs[k] + lo + i);
+    scratch[i] = a * scale;
+  }
+}
+
+// bufs[k][i] = scratch[i - lo] for every rank k, i in [lo, hi)
+__global__ void __launch_bounds__(256)
+k_broadcast_slice(float* const* __restrict__ bufs, int world, int64_t lo, int64_t hi, const float* __restrict__ scratch) {
+  pdl_prologue();
+  const int64_t n = hi - lo;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(bufs[0] + lo) & 15) == 0) ? n / 4 : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(scratch)[i];
+    for (int k = 0; k < world; ++k) reinterpret_cast<float4*>(bufs[k] + lo)[i] = v;
+  }
+  for (int64_t i = 4 * n4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = scratch[i];
+    for (int k = 0; k < world; ++k) bufs[k][lo + i] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t pgnn_allreduce_p2p_scratch_floats(int64_t n, int world) {
+  if (n < 0 || world < 1) return PGNN_EINVAL;
+  return align_up(ceil_div(n, world), 4);
+}
+
+int pgnn_allreduce_p2p(void* const* bufs, void* const* flags, int rank, int world, int64_t n, float scale, float* scratch,
+                       int64_t scratch_floats, int64_t epoch, void* stream) {
+  PGNN_CHECK_ARG(bufs && flags && world >= 1 && world <= 32 && rank >= 0 && rank < world && n >= 0 && epoch >= 0);
+  if (world == 1 && scale == 1.f) return PGNN_OK;
+  const int64_t chunk = pgnn_allreduce_p2p_scratch_floats(n, world);  // multiple of 4: slice starts keep the buffer's alignment
+  PGNN_CHECK_ARG(scratch || n == 0);
+  if (scratch_floats < chunk) return PGNN_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  float* const* b = reinterpret_cast<float* const*>(bufs);
+  uint32_t* const* f = reinterpret_cast<uint32_t* const*>(flags);
+  const uint32_t seq = (uint32_t)(3 * epoch);  // three barriers per call; the caller passes epoch = 0, 1, 2, ...
+  const int64_t lo = chunk * rank < n ? chunk * rank : n;
+  const int64_t hi = lo + chunk < n ? lo + chunk : n;
+  const int64_t work = ceil_div(hi - lo, 4 * 256);
+  const unsigned blocks = (unsigned)(work < 1 ? 1 : work > 2 * kNumSMs ? 2 * kNumSMs : work);
+  PGNN_CUDA(pgnn_launch(k_xgpu_barrier, dim3(1), dim3(32), 0, st, f, rank, world, seq + 1));
+  PGNN_LAUNCH_CHECK();
+  PGNN_CUDA(pgnn_launch(k_reduce_slice, dim3(blocks), dim3(256), 0, st, b, world, lo, hi, scale, scratch));
+  PGNN_LAUNCH_CHECK();
+  PGNN_CUDA(pgnn_launch(k_xgpu_barrier, dim3(1), dim3(32), 0, st, f, rank, world, seq + 2));
+  PGNN_LAUNCH_CHECK();
+  PGNN_CUDA(pgnn_launch(k_broadcast_slice, dim3(blocks), dim3(256), 0, st, b, world, lo, hi, (const float*)scratch));
+  PGNN_LAUNCH_CHECK();
+  PGNN_CUDA(pgnn_launch(k_xgpu_barrier, dim3(1), dim3(32), 0, st, f, rank, world, seq + 3));
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
+}  // extern "C"

@@ -2,10 +2,19 @@
 
 The reference has no parallelism at all; graphs in a batch are independent, so the
 path shards by graph with no activation exchange and the only collective is the gradient all-reduce
-(section 8(e)).  Each rank's BatchNorm statistics are local (like DDP without SyncBN).  Backend: NCCL on
-GPUs (NVLink 5 / NVSwitch), gloo in the CPU tests.
+(section 8(e)).  Each rank's BatchNorm statistics are local (like DDP without SyncBN).
+
+Two transports for that all-reduce:
+  * "p2p"  -- this library's own kernels over NVLink peer memory (csrc/collective.cu): the gradients are written by the
+              backward pass straight into a symmetric allocation, reduce-scattered with peer loads and all-gathered with
+              peer stores, three flag barriers, bit-identical on every rank.  torch.distributed's symmetric-memory
+              allocator is used for what it is: allocation and the exchange of peer addresses.
+  * "nccl" -- torch.distributed.all_reduce (NCCL on GPUs, gloo in the CPU tests), with the head's small buffer launched
+              from a gradient hook so that it overlaps the encoder's backward.
 """
 from __future__ import annotations
+
+import sys
 
 import torch
 import torch.distributed as dist
@@ -18,52 +27,219 @@ def shard_graphs(num_graphs: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _flat_is_live(flat, params):
+    """True when every parameter's .grad is the contiguous view of `flat` at its running offset, i.e. all-reducing `flat`
+    in place all-reduces the gradients.  False e.g. after autograd ACCUMULATED a new backward into older gradient tensors."""
+    if flat is None:
+        return False
+    at = flat.data_ptr()
+    for p in params:
+        g = p.grad
+        if g is None or g.data_ptr() != at or not g.is_contiguous():
+            return False
+        at += 4 * p.numel()
+    return True
+
+
+def _pack(views, params):
+    torch._foreach_copy_(views, [p.grad if p.grad is not None else torch.zeros_like(p) for p in params])
+
+
+def _unpack(views, params):
+    for p, v in zip(params, views):
+        if p.grad is None:
+            p.grad = v.clone()
+    torch._foreach_copy_([p.grad for p in params], views)
+
+
+class P2PAllReduce:
+    """A symmetric fp32 buffer of `numel` elements plus the flag words of `pgnn_allreduce_p2p`."""
+
+    FLAG_FLOATS = 64  # 256 bytes in front of the data: keeps the data 16-byte aligned, room for 64 ranks' flag words
+
+    def __init__(self, numel, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from ._cabi import lib
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world, self.numel = dist.get_rank(group), dist.get_world_size(group), int(numel)
+        self.sym = symm.empty(self.FLAG_FLOATS + self.numel, dtype=torch.float32, device=device)
+        self.sym.zero_()
+        hdl = symm.rendezvous(self.sym, group)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self._hdl = hdl
+        self.buf = self.sym[self.FLAG_FLOATS:]
+        self.flag_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.buf_ptrs = torch.tensor([p + 4 * self.FLAG_FLOATS for p in ptrs], dtype=torch.int64, device=device)
+        nscratch = lib.pgnn_allreduce_p2p_scratch_floats(self.numel, self.world)
+        self.scratch = torch.empty(max(int(nscratch), 4), dtype=torch.float32, device=device)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's zeroed flag words are in place before anyone signals
+
+    def run(self, scale=1.0):
+        from ._cabi import check, lib
+        check(lib.pgnn_allreduce_p2p(self.buf_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.numel,
+                                     float(scale), self.scratch.data_ptr(), self.scratch.numel(), self.epoch,
+                                     torch.cuda.current_stream(self.sym.device).cuda_stream), "pgnn_allreduce_p2p")
+        self.epoch += 1
+        return self.buf
+
+
 class GradAllReducer:
-    """One all-reduce per flat gradient buffer.
+    """One all-reduce of every gradient per step.
 
-    The fused encoder already leaves its gradients in ONE flat fp32 buffer (`plan.last_flat_grad`, every
-    `p.grad` of the encoder is a view of it): those buffers are all-reduced in place, nothing is packed.
-    The remaining parameters (heads) are packed into a second small buffer.  7.4 MB for chem GIN: a
-    latency-bound collective on NVLink 5 / NVSwitch instead of 42 small ones."""
+    `flat_sources`: callables returning (flat_tensor, [params it covers]) for modules whose backward already leaves its
+    gradients in ONE flat fp32 buffer (the fused encoder: every `p.grad` is a view of it).  The remaining parameters
+    (heads) are packed into a small buffer.
 
-    def __init__(self, params, flat_sources=(), group=None):
-        self.group = group
-        self.flat_sources = list(flat_sources)  # callables returning (flat_tensor, [params it covers])
+    backend "p2p": one symmetric buffer holds [flat sources | packed rest]; flat sources that can be bound
+    (`src.bind(buffer)`) write their gradients straight into it, so the step is: backward -> copy the head's two tensors in
+    -> `pgnn_allreduce_p2p` -> copy them out.  backend "nccl": the flat buffers are all-reduced in place by
+    torch.distributed; with `overlap=True` the packed buffer's all-reduce is launched from a gradient hook as soon as the
+    last of its parameters has a gradient, i.e. under the encoder's backward (one backward per all_reduce_mean call).
+    backend "auto": p2p on CUDA when the symmetric-memory rendezvous works, else nccl (reported on stderr).
+
+    `scale=False` leaves the SUM in place (pass `grad_scale=1/world` to `optim.Adam` instead)."""
+
+    def __init__(self, params, flat_sources=(), group=None, overlap=True, scale=True, backend="auto"):
+        self.group, self.scale = group, scale
+        self.flat_sources = list(flat_sources)
         covered = set()
         for src in self.flat_sources:
             covered.update(id(p) for p in src()[1])
         self.params = [p for p in params if p.requires_grad and id(p) not in covered]
         self.sizes = [p.numel() for p in self.params]
-        self.flat = None
-        if self.params:
+        self.flat, self._pending, self._seen, self._hooks, self.p2p = None, None, 0, [], None
+        all_params = self.params + [p for src in self.flat_sources for p in src()[1]]
+        on_cuda = bool(all_params) and all(p.is_cuda for p in all_params)
+        if backend not in ("auto", "p2p", "nccl"):
+            raise ValueError("backend must be 'auto', 'p2p' or 'nccl'")
+        if backend == "p2p" and not on_cuda:
+            raise ValueError("the p2p all-reduce needs CUDA parameters")
+        self.backend = "nccl"
+        if backend != "nccl" and on_cuda and dist.get_world_size(group) > 1:
+            try:
+                self._setup_p2p(all_params[0].device)
+                self.backend = "p2p"
+            except Exception as e:  # no peer access / symmetric memory unavailable on this box
+                if backend == "p2p":
+                    raise
+                print("[pretrain_gnns_b200.dist] p2p all-reduce unavailable (%s: %s); using torch.distributed" % (type(e).__name__, e),
+                      file=sys.stderr, flush=True)
+                self.p2p = None
+        if self.backend == "nccl" and self.params:
             self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
             self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+            if overlap:
+                for p in self.params:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # ---- p2p transport ----------------------------------------------------------------------------------------------
+    def _setup_p2p(self, device):
+        src_sizes = [sum(p.numel() for p in src()[1]) for src in self.flat_sources]
+        pad4 = lambda n: (n + 3) // 4 * 4  # every region starts 16-byte aligned
+        offs, tot = [], 0
+        for n in src_sizes + [sum(self.sizes)]:
+            offs.append(tot)
+            tot += pad4(n)
+        self.p2p = P2PAllReduce(tot, device, self.group)
+        self.regions = [self.p2p.buf[o:o + n] for o, n in zip(offs[:-1], src_sizes)]
+        self.region_views = [[v.view_as(p) for v, p in zip(r.split([p.numel() for p in src()[1]]), src()[1])]
+                             for src, r in zip(self.flat_sources, self.regions)]
+        for src, region in zip(self.flat_sources, self.regions):
+            if hasattr(src, "bind"):
+                src.bind(region)
+        self.flat = self.p2p.buf[offs[-1]:offs[-1] + sum(self.sizes)] if self.params else None
+        if self.params:
+            self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+
+    def _all_reduce_p2p(self, inv):
+        after = []
+        for src, region, views in zip(self.flat_sources, self.regions, self.region_views):
+            flat, ps = src()
+            if _flat_is_live(flat, ps):
+                if flat.data_ptr() != region.data_ptr():  # live, but somewhere else: one bulk copy each way
+                    region.copy_(flat)
+                    after.append(lambda flat=flat, region=region: flat.copy_(region))
+            else:  # e.g. gradients accumulated over several backward passes: the parameters' .grad are the truth
+                _pack(views, ps)
+                after.append(lambda views=views, ps=ps: _unpack(views, ps))
+        if self.params:
+            _pack(self.views, self.params)
+        self.p2p.run(inv if self.scale else 1.0)
+        for fn in after:
+            fn()
+        if self.params:
+            _unpack(self.views, self.params)
+        return self.flat
+
+    # ---- torch.distributed transport --------------------------------------------------------------------------------
+    def _on_grad(self, _param):
+        self._seen += 1
+        if self._seen == len(self.params) and self._pending is None:
+            self._launch_packed()
+
+    def _launch_packed(self):
+        _pack(self.views, self.params)
+        self._pending = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def all_reduce_mean(self):
+        """Call after loss.backward().  Returns the packed buffer of the non-flat parameters (or None)."""
         world = dist.get_world_size(self.group)
         inv = 1.0 / world
+        if self.backend == "p2p":
+            return self._all_reduce_p2p(inv)
+        works = []
         for src in self.flat_sources:
-            flat, _ = src()
-            if flat is not None:
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-                flat.mul_(inv)
+            flat, ps = src()
+            unpack = None
+            if not _flat_is_live(flat, ps):  # fall back to packing this module's gradients
+                if not ps:
+                    continue
+                flat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+                views = [v.view_as(p) for v, p in zip(flat.split([p.numel() for p in ps]), ps)]
+                _pack(views, ps)
+                unpack = (views, ps)
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat, unpack))
         if self.flat is not None:
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-            torch._foreach_copy_(self.views, grads)
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(inv)
-            for p, v in zip(self.params, self.views):
-                if p.grad is None:
-                    p.grad = v.clone()
-            torch._foreach_copy_([p.grad for p in self.params], self.views)
+            if self._pending is None:  # no hooks, or a parameter got no gradient this step
+                self._launch_packed()
+            self._pending.wait()
+            self._pending, self._seen = None, 0
+            if self.scale:
+                self.flat.mul_(inv)
+            _unpack(self.views, self.params)
+        for work, flat, unpack in works:
+            work.wait()
+            if self.scale:
+                flat.mul_(inv)
+            if unpack is not None:
+                _unpack(*unpack)
         return self.flat
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for src in self.flat_sources:
+            if self.p2p is not None and hasattr(src, "bind"):
+                src.bind(None)
 
 
 def encoder_flat_source(gnn):
-    """flat_sources entry for a chem GNN running the fused path: (last flat gradient buffer, its parameters)."""
+    """flat_sources entry for a chem GNN running the fused path: (last flat gradient buffer, its parameters).
+    `bind(buffer)` makes the encoder's backward write its gradients into `buffer` (see ChemGinPlan.grad_buffer)."""
     def src():
         plan = gnn._fused_plan()
         if plan is None:
             return None, []
         return plan.last_flat_grad, plan.params
+
+    def bind(buffer):
+        plan = gnn._fused_plan()
+        if plan is not None:
+            if buffer is not None and buffer.numel() != plan.total:
+                raise ValueError("bound gradient buffer does not match the encoder's flat layout")
+            plan.grad_buffer = buffer
+    src.bind = bind
     return src

@@ -588,6 +588,9 @@ class ChemGinPlan:
         self.BnArr = _ct.c_void_p * self.L
         self.bns = list(gnn.batch_norms)
         self.last_flat_grad = None  # the flat gradient buffer of the most recent backward (all-reduce target)
+        # optional caller-owned destination ([total] fp32, e.g. a slice of NVLink-symmetric memory): used instead of a fresh
+        # buffer whenever no parameter still holds a gradient (autograd would otherwise add a view of the buffer to itself)
+        self.grad_buffer = None
 
 
 class _ChemGinEncoder(Function):
@@ -630,7 +633,10 @@ class _ChemGinEncoder(Function):
         plan = ctx.plan
         N, E, L, D = ctx.dims
         g = _f32(g)
-        flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
+        if plan.grad_buffer is not None and all(p.grad is None for p in plan.params):
+            flat = plan.grad_buffer
+        else:
+            flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
         check(lib.pgnn_chem_gin_backward(ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), N, E, L, D, _precision, _p(flat), _p(ctx.ws),
                                          ctx.wsb, _st()), "chem_gin_backward")
         plan.last_flat_grad = flat

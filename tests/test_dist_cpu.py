@@ -29,9 +29,28 @@ def _worker(rank, world, port, out):
     rep = O.chem_gnn(P, b["x"], b["edge_index"], b["edge_attr"], 2, "gin", True)
     rep.square().mean().backward()
     local = [p.grad.clone() for p in params]
-    red = pdist.GradAllReducer(params)
+    red = pdist.GradAllReducer(params, overlap=False)
     red.all_reduce_mean()
-    torch.save({"local": local, "reduced": [p.grad.clone() for p in params]}, os.path.join(out, f"r{rank}.pt"))
+    res = {"local": local, "reduced": [p.grad.clone() for p in params]}
+
+    # second step through the overlapped route: the first 4 tensors stand in for the fused encoder (their gradients are
+    # views of one flat buffer, reduced in place), the rest are packed and launched from the gradient hooks
+    flat_params, rest = params[:4], params[4:]
+    state = {"flat": None}
+    red2 = pdist.GradAllReducer(params, flat_sources=[lambda: (state["flat"], flat_params)], overlap=True)
+    for p in params:
+        p.grad = None
+    rep = O.chem_gnn(P, b["x"], b["edge_index"], b["edge_attr"], 2, "gin", True)
+    (2.0 * rep.square().mean()).backward()
+    assert red2._pending is not None  # launched from the hooks, before all_reduce_mean is called
+    state["flat"] = torch.cat([p.grad.reshape(-1) for p in flat_params])
+    for p, v in zip(flat_params, state["flat"].split([p.numel() for p in flat_params])):
+        p.grad = v.view_as(p)
+    res["local2"] = [p.grad.clone() for p in params]
+    red2.all_reduce_mean()
+    res["reduced2"] = [p.grad.clone() for p in params]
+    red2.close()
+    torch.save(res, os.path.join(out, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -40,6 +59,9 @@ def test_flat_grad_allreduce_is_mean_of_shards(tmp_path):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r = [torch.load(os.path.join(tmp_path, f"r{k}.pt")) for k in range(world)]
     for a, b, m0, m1 in zip(r[0]["local"], r[1]["local"], r[0]["reduced"], r[1]["reduced"]):
+        assert torch.allclose(m0, (a + b) / 2, atol=1e-7, rtol=1e-6)
+        assert torch.equal(m0, m1)
+    for a, b, m0, m1 in zip(r[0]["local2"], r[1]["local2"], r[0]["reduced2"], r[1]["reduced2"]):
         assert torch.allclose(m0, (a + b) / 2, atol=1e-7, rtol=1e-6)
         assert torch.equal(m0, m1)
 
