@@ -253,6 +253,7 @@ def run_b200(args, rank, world, local_rank):
 
     def timed(e2e):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()  # ranks finish their (CPU-side) setup seconds apart; start the first exchange together
         for i in range(args.warmup):
             b = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % len(pinned)].items()} if e2e else resident[i % len(resident)]
             step(b).item()

@@ -300,7 +300,7 @@ PGNN_API int pgnn_adam_step(const PgnnAdamChunk* chunks, int64_t num_chunks, dou
  *   scratch: local device buffer of pgnn_allreduce_p2p_scratch_floats(n, world) floats
  *   epoch : 0, 1, 2, ... incremented by the caller on every call, identical on all ranks
  * On return (stream order) every rank's buffer holds scale * sum over ranks.  A rank that never arrives traps the waiting
- * kernels after ~2 s (sticky CUDA error) instead of hanging. */
+ * kernels after ~60 s (sticky CUDA error) instead of hanging. */
 PGNN_API int64_t pgnn_allreduce_p2p_scratch_floats(int64_t n, int world);
 PGNN_API int pgnn_allreduce_p2p(void* const* bufs, void* const* flags, int rank, int world, int64_t n, float scale,
                                 float* scratch, int64_t scratch_floats, int64_t epoch, void* stream);

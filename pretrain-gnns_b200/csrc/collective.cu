@@ -12,7 +12,8 @@
 // Each element is summed by exactly one rank in the order 0..G-1, so all ranks end with bit-identical gradients and the
 // result does not depend on timing.  A cross-GPU barrier is a one-CTA kernel: thread t publishes a monotonically increasing
 // sequence number to rank t's flag word [rank] (st.release.sys after a system fence) and spins on its own flag word [t]
-// (ld.acquire.sys, time-bounded: a lost peer traps after ~2 s instead of hanging the GPU).  Kernel boundaries order the
+// (ld.acquire.sys, time-bounded: a lost peer traps after ~60 s instead of hanging the GPU; the bound is generous because ranks
+// may reach their first exchange seconds apart -- module loading, first-touch allocations).  Kernel boundaries order the
 // phases inside a GPU.  For the 7.4 MB chem-GIN buffer on 2 GPUs this replaces a ~180 us NCCL call.
 #include "common.cuh"
 
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(32) k_xgpu_barrier(uint32_t* const* __restrict
       uint32_t v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - seq) >= 0) break;
-      if ((it & 255u) == 255u && gtimer_ns() - t0 > 2000000000ull) asm volatile("trap;");
+      if ((it & 255u) == 255u && gtimer_ns() - t0 > 60000000000ull) asm volatile("trap;");
     }
   }
 }
