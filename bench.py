@@ -34,7 +34,7 @@ BATCH = 256
 NUM_LAYER, EMB = 5, 300
 NUM_DISTINCT_BATCHES = 8
 METRIC = "graphs/sec 5-layer GIN-300 fwd+bwd on ZINC-shaped batches"
-GEMM1_DRAM_BYTES_NCU = 7952896  # ncu capture of the B=256 GEMM1 launch (profiles/r01_gemm_ncu.md)
+GEMM1_DRAM_BYTES_NCU = 7956992  # dram__bytes_read.sum + dram__bytes_write.sum of the B=256 GEMM1 launch (profiles/r01_gemm_tma_ncu.md)
 
 
 def peaks():
@@ -284,7 +284,7 @@ def run_b200(args, rank, world, local_rank):
     graphs = BATCH * world * args.steps
 
     roof, roof_gather = kernel_rooflines(ops, cabi, resident[0], dev) if rank == 0 else (None, None)
-    cpu = cpu_oracle_run(6, 2, batches=host[:2]) if rank == 0 and not args.no_cpu_baseline else None
+    cpu = cpu_oracle_run(6, 2, batches=host[:2]) if rank == 0 and world == 1 and not args.no_cpu_baseline else None  # N=1 only
     if rank != 0:
         return
     line = {
@@ -342,7 +342,7 @@ def kernel_rooflines(ops, cabi, b, dev):
     roof = {"bound": "tensor", "kernel": "MLP GEMM1 [N,300]x[300,600] + bias + ReLU (%s; k_gemm_3xtf32_tma<0,0,224>)" % mode,
             "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at these shapes, one `ncu --set full` capture
-            # (profiles/r01_gemm_ncu.md): 7.95 MB read + 0.0003 MB written inside the kernel window; algorithmic 7.18 + 0.72 MB
+            # (profiles/r01_gemm_tma_ncu.md): 7.96 MB read + 0 B written inside the kernel window; algorithmic 7.18 + 0.72 MB
             "traffic": GEMM1_DRAM_BYTES_NCU,
             "peak_source": pk["src"] + " cuBLAS bf16 dense burst (MEASURED_PEAKS.json)",
             "note": "fp32-equivalent flops; 3xTF32 spends 3 tf32 MACs per fp32 MAC and dense tf32 is half of bf16, so the "
@@ -365,8 +365,8 @@ def main():
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20  # bounded sample: ~0.2-0.3 s per CPU step
+        if args.steps > 500:
+            args.steps = 500  # bounded sample: ~0.1 s per CPU step at the best thread count
         run_reference(args, rank)
         return
     if args.warmup < 3:
