@@ -42,6 +42,12 @@ PGNN_API const char* pgnn_error_string(int code);
 PGNN_API int pgnn_last_cuda_error(void);          /* cudaError_t of the last PGNN_ECUDA on this thread */
 PGNN_API int pgnn_device_sm_count(int device);   /* host query; negative on error */
 PGNN_API int64_t pgnn_kernel_launch_count(void); /* kernels this library has enqueued since load (process-wide) */
+/* Per-kernel timing mode: while enabled, every kernel launch of the library is bracketed by a CUDA event pair on its own
+ * stream (this serialises neighbouring kernels: use it for a few diagnostic steps, not for the number you report).
+ * pgnn_profile_read waits for the recorded events, writes "kernel name<TAB>launches<TAB>total_us" lines into buf
+ * (host memory, NUL-terminated, truncated to buflen), clears the records and returns the number of launches covered. */
+PGNN_API int pgnn_profile_enable(int on);
+PGNN_API int64_t pgnn_profile_read(char* buf, int64_t buflen);
 
 /* ---------------------------------------------------------------------------------------------
  * Graph preparation (integer, bit-exact).  Replaces the per-layer, per-edge gather / scatter_add

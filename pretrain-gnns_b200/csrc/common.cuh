@@ -8,6 +8,10 @@
 #include <utility>
 extern thread_local int g_pgnn_last_cuda_error;
 extern std::atomic<long long> g_pgnn_kernel_launches;  // every kernel this library enqueues (pgnn_kernel_launch_count)
+// Per-kernel timing mode (pgnn_profile_enable): every launch is bracketed by a CUDA event pair on its own stream, so that
+// a caller can read each kernel's duration inside the real step (warm L2, true operand residency) without a profiler.
+extern std::atomic<int> g_pgnn_profile_on;
+void pgnn_profile_mark(const void* kernel, cudaStream_t st, bool after);
 
 #define PGNN_CHECK_ARG(cond)            \
   do {                                  \
@@ -130,7 +134,11 @@ inline cudaError_t pgnn_launch_cluster_x(void (*kernel)(KArgs...), dim3 grid, di
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  const bool prof = g_pgnn_profile_on.load(std::memory_order_relaxed) != 0;
+  if (prof) pgnn_profile_mark(reinterpret_cast<const void*>(kernel), st, false);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (prof) pgnn_profile_mark(reinterpret_cast<const void*>(kernel), st, true);
+  return err;
 }
 
 template <typename... KArgs, typename... Args>
@@ -145,7 +153,11 @@ inline cudaError_t pgnn_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  const bool prof = g_pgnn_profile_on.load(std::memory_order_relaxed) != 0;
+  if (prof) pgnn_profile_mark(reinterpret_cast<const void*>(kernel), st, false);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (prof) pgnn_profile_mark(reinterpret_cast<const void*>(kernel), st, true);
+  return err;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
