@@ -13,7 +13,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(_HERE, "..", "include", "pgnn_b200.h")
-LIB_PATH = os.path.join(_HERE, "libpgnn_b200.so")
+LIB_PATH = os.environ.get("PGNN_LIB") or os.path.join(_HERE, "libpgnn_b200.so")  # PGNN_LIB: development builds (tools/)
 
 _SCALARS = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "float": ctypes.c_float, "double": ctypes.c_double,
             "void": None}

@@ -22,6 +22,10 @@
 // SM takes 264 KB per 32-deep block down to 180 KB at BN = 224.  Protocol differences: the converters of BOTH CTAs
 // arrive on the LEADER's lo_full (remote mbarrier arrive, release.cluster, after a generic->async proxy fence), and the
 // leader's commits are multicast to both CTAs' lo_empty / raw_empty / acc_bar.
+//
+// Decomposition builds (tools/ubench_gemm.py; never defined in the product build): PGNN_UB_NO_TMA (stages "land" without a
+// copy), PGNN_UB_NO_CONVERT (lo stages are published unconverted), PGNN_UB_NO_MMA (stages are committed back without MMAs),
+// PGNN_UB_NO_EPILOGUE.  Results are garbage; the timings isolate what each role costs under full-chip load.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -196,6 +200,10 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NRAW;
         if (kb >= NRAW) mbar_wait(smem_u32(&raw_empty[s]), ((kb / NRAW) - 1) & 1);
+#ifdef PGNN_UB_NO_TMA
+        mbar_arrive(smem_u32(&raw_full[s]));
+        continue;
+#endif
         mbar_expect_tx(smem_u32(&raw_full[s]), Cfg::STAGE);  // a box is always written in full (zero-filled out of bounds)
         const int k0 = kbeg + kb * TBK;
         const uint32_t bar = smem_u32(&raw_full[s]), da = smem_u32(raw(kb)), db = da + Cfg::A_BYTES;
@@ -228,6 +236,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (kb == nkb - 1) TC_TRACE(5);
         if (lane == 0) {
           const uint32_t ah = smem_u32(raw(kb)), bh = ah + Cfg::A_BYTES, al = smem_u32(lo(kb)), bl = al + Cfg::A_BYTES;
+#ifndef PGNN_UB_NO_MMA
 #pragma unroll
           for (int j = 0; j < TBK / 8; ++j) {
             const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
@@ -241,6 +250,9 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               umma_tf32(tmem_acc, tma_desc<A_MN>(ah, j), tma_desc<B_MN>(bh, j), idesc, first);
             }
           }
+#else
+          (void)ah; (void)bh; (void)al; (void)bl;
+#endif
           if (PAIR) {  // both CTAs' stages were read by these MMAs: release them in both
             umma_commit_pair(smem_u32(&lo_empty[kb % T_NLO]));
             umma_commit_pair(smem_u32(&raw_empty[kb % NRAW]));
@@ -263,6 +275,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (kb >= T_NLO) mbar_wait(smem_u32(&lo_empty[kb % T_NLO]), ((kb / T_NLO) - 1) & 1);
       const float4* src = reinterpret_cast<const float4*>(raw(kb));
       float4* dst = reinterpret_cast<float4*>(lo(kb));
+#ifndef PGNN_UB_NO_CONVERT
 #pragma unroll 4
       for (int i = threadIdx.x; i < V4; i += NPRODUCER) {
         const float4 v = src[i];
@@ -273,6 +286,9 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
         dst[i] = l;
       }
+#else
+      (void)src; (void)dst; (void)V4;
+#endif
       if (PAIR) fence_async_smem();  // writer-side proxy fence: the peer CTA's tensor-core reads are ordered through a remote arrive
       __syncwarp();
       if (lane == 0) {
@@ -287,7 +303,9 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
     if (warp == 0) TC_TRACE(6);
+#ifndef PGNN_UB_NO_EPILOGUE
     tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
+#endif
     if (warp == 0) TC_TRACE(7);
   }
   tc_fence_before();
