@@ -310,6 +310,11 @@ PGNN_API int pgnn_adam_step(const PgnnAdamChunk* chunks, int64_t num_chunks, dou
 PGNN_API int64_t pgnn_allreduce_p2p_scratch_floats(int64_t n, int world);
 PGNN_API int pgnn_allreduce_p2p(void* const* bufs, void* const* flags, int rank, int world, int64_t n, float scale,
                                 float* scratch, int64_t scratch_floats, int64_t epoch, void* stream);
+/* EXPERIMENTAL, not yet measured on hardware and not used by default: the same exchange with the NVSwitch doing the sum
+ * (multimem.ld_reduce / multimem.st on the multicast mapping `mc_buf` of the symmetric buffer).  n % (4*world) == 0;
+ * two flag barriers per call (own epoch counter; do not share a flag array with pgnn_allreduce_p2p). */
+PGNN_API int pgnn_allreduce_nvls(float* mc_buf, void* const* flags, int rank, int world, int64_t n, float scale,
+                                 int64_t epoch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,9 +82,50 @@ k_broadcast_slice(float* const* __restrict__ bufs, int world, int64_t lo, int64_
   }
 }
 
+// NVLS form of the two middle phases: one multimem.ld_reduce per 16 bytes fetches the sum over all ranks from the switch,
+// one multimem.st stores it (scaled) into every rank's buffer.  Rank r is the only one that reads or writes slice r, so no
+// barrier is needed between the two.  `mc` is the multicast address of the symmetric buffer.
+__global__ void __launch_bounds__(256) k_nvls_reduce_bcast_slice(float* __restrict__ mc, int64_t lo, int64_t hi, float scale) {
+  pdl_prologue();
+  const int64_t n4 = (hi - lo) / 4;  // the caller guarantees 16-byte aligned slices of whole float4s
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float* p = mc + lo + 4 * i;
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// EXPERIMENTAL (not yet measured on hardware; nothing calls it by default): the all-reduce above with the switch doing the
+// reduction.  n must be a multiple of 4 * world and the buffer 16-byte aligned; `mc_buf` is the multicast mapping of the
+// same symmetric buffer, `flags` as for pgnn_allreduce_p2p (two barriers per call: pass epoch counting calls of THIS function
+// and do not mix the two functions on one flag array).
+int pgnn_allreduce_nvls(float* mc_buf, void* const* flags, int rank, int world, int64_t n, float scale, int64_t epoch, void* stream) {
+  PGNN_CHECK_ARG(mc_buf && flags && world >= 1 && world <= 32 && rank >= 0 && rank < world && n >= 0 && epoch >= 0);
+  PGNN_CHECK_ARG(n % (4 * (int64_t)world) == 0 && (reinterpret_cast<uintptr_t>(mc_buf) & 15) == 0);
+  cudaStream_t st = as_stream(stream);
+  uint32_t* const* f = reinterpret_cast<uint32_t* const*>(flags);
+  const uint32_t seq = (uint32_t)(2 * epoch);
+  const int64_t chunk = n / world, lo = chunk * rank, hi = lo + chunk;
+  const int64_t work = ceil_div(chunk, 4 * 256);
+  const unsigned blocks = (unsigned)(work < 1 ? 1 : work > 2 * kNumSMs ? 2 * kNumSMs : work);
+  PGNN_CUDA(pgnn_launch(k_xgpu_barrier, dim3(1), dim3(32), 0, st, f, rank, world, seq + 1));
+  PGNN_LAUNCH_CHECK();
+  PGNN_CUDA(pgnn_launch(k_nvls_reduce_bcast_slice, dim3(blocks), dim3(256), 0, st, mc_buf, lo, hi, scale));
+  PGNN_LAUNCH_CHECK();
+  PGNN_CUDA(pgnn_launch(k_xgpu_barrier, dim3(1), dim3(32), 0, st, f, rank, world, seq + 2));
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
 
 int64_t pgnn_allreduce_p2p_scratch_floats(int64_t n, int world) {
   if (n < 0 || world < 1) return PGNN_EINVAL;

@@ -53,34 +53,55 @@ def _unpack(views, params):
 
 
 class P2PAllReduce:
-    """A symmetric fp32 buffer of `numel` elements plus the flag words of `pgnn_allreduce_p2p`."""
+    """A symmetric fp32 buffer of `numel` elements plus the flag words of `pgnn_allreduce_p2p`.
 
-    FLAG_FLOATS = 64  # 256 bytes in front of the data: keeps the data 16-byte aligned, room for 64 ranks' flag words
+    `nvls=True` (or PGNN_ALLREDUCE=nvls; EXPERIMENTAL, not yet measured) routes `run` through `pgnn_allreduce_nvls`: the
+    NVSwitch performs the sum (multimem.ld_reduce on the buffer's multicast mapping).  Falls back to the peer-load kernels
+    when the allocation has no multicast mapping."""
 
-    def __init__(self, numel, device, group=None):
+    FLAG_FLOATS = 64  # 256 bytes in front of the data: keeps the data 16-byte aligned; words [0,32) p2p flags, [32,64) nvls flags
+
+    def __init__(self, numel, device, group=None, nvls=None):
+        import os
         import torch.distributed._symmetric_memory as symm
         from ._cabi import lib
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world, self.numel = dist.get_rank(group), dist.get_world_size(group), int(numel)
-        self.sym = symm.empty(self.FLAG_FLOATS + self.numel, dtype=torch.float32, device=device)
+        if nvls is None:
+            nvls = os.environ.get("PGNN_ALLREDUCE", "") == "nvls"
+        quantum = 4 * self.world
+        self.padded = (self.numel + quantum - 1) // quantum * quantum  # the nvls kernel works on whole float4s per rank
+        self.sym = symm.empty(self.FLAG_FLOATS + self.padded, dtype=torch.float32, device=device)
         self.sym.zero_()
         hdl = symm.rendezvous(self.sym, group)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         self._hdl = hdl
-        self.buf = self.sym[self.FLAG_FLOATS:]
+        self.buf = self.sym[self.FLAG_FLOATS:self.FLAG_FLOATS + self.numel]
         self.flag_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
         self.buf_ptrs = torch.tensor([p + 4 * self.FLAG_FLOATS for p in ptrs], dtype=torch.int64, device=device)
         nscratch = lib.pgnn_allreduce_p2p_scratch_floats(self.numel, self.world)
         self.scratch = torch.empty(max(int(nscratch), 4), dtype=torch.float32, device=device)
         self.epoch = 0
+        self.mc_buf = None
+        if nvls:
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if getattr(hdl, "has_multicast_support", lambda *a: True) else 0
+            if mc and self.world <= 32:
+                self.mc_buf = mc + 4 * self.FLAG_FLOATS
+                self.nvls_flag_ptrs = torch.tensor([p + 128 for p in ptrs], dtype=torch.int64, device=device)
+        self.transport = "nvls" if self.mc_buf else "p2p"
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's zeroed flag words are in place before anyone signals
 
     def run(self, scale=1.0):
         from ._cabi import check, lib
-        check(lib.pgnn_allreduce_p2p(self.buf_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.numel,
-                                     float(scale), self.scratch.data_ptr(), self.scratch.numel(), self.epoch,
-                                     torch.cuda.current_stream(self.sym.device).cuda_stream), "pgnn_allreduce_p2p")
+        st = torch.cuda.current_stream(self.sym.device).cuda_stream
+        if self.mc_buf:
+            check(lib.pgnn_allreduce_nvls(self.mc_buf, self.nvls_flag_ptrs.data_ptr(), self.rank, self.world, self.padded, float(scale),
+                                          self.epoch, st), "pgnn_allreduce_nvls")
+        else:
+            check(lib.pgnn_allreduce_p2p(self.buf_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.numel,
+                                         float(scale), self.scratch.data_ptr(), self.scratch.numel(), self.epoch, st),
+                  "pgnn_allreduce_p2p")
         self.epoch += 1
         return self.buf
 
@@ -120,7 +141,7 @@ class GradAllReducer:
         if backend != "nccl" and on_cuda and dist.get_world_size(group) > 1:
             try:
                 self._setup_p2p(all_params[0].device)
-                self.backend = "p2p"
+                self.backend = self.p2p.transport  # "p2p", or "nvls" when opted in
             except Exception as e:  # no peer access / symmetric memory unavailable on this box
                 if backend == "p2p":
                     raise
@@ -187,7 +208,7 @@ class GradAllReducer:
         """Call after loss.backward().  Returns the packed buffer of the non-flat parameters (or None)."""
         world = dist.get_world_size(self.group)
         inv = 1.0 / world
-        if self.backend == "p2p":
+        if self.p2p is not None:
             return self._all_reduce_p2p(inv)
         works = []
         for src in self.flat_sources:
