@@ -44,10 +44,10 @@ struct TmaCfg {
   static constexpr int A_BYTES = BM * TBK * 4;  // 16 KiB (either major: R rows x 32 k x 4 B)
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TBK * 4;  // per CTA
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  // Ring depths.  The main loop is a latency chain, not a bandwidth limit: a raw stage is refilled only after the MMAs that read
-  // it complete (commit -> TMA issue -> TMA latency -> conversion -> arrive -> MMA: ~2.5 us), a lo stage likewise (~1.7 us), so
-  // a block costs max(tensor time, 2.5 us / NRAW, 1.7 us / NLO).  Measured at BN = 224: 1.22 us per block with 2 + 2 stages
-  // against 0.70 us of tensor time.  As many stages as 220 KiB hold, at most 4 + 4.
+  // Ring depths.  A raw stage is refilled only after the MMAs that read it complete (commit -> TMA issue -> TMA latency ->
+  // conversion -> arrive -> MMA: ~3 us round trip), a lo stage likewise (~2 us), so a block costs at least
+  // max(tensor time, 3 us / NRAW, 2 us / NLO).  Measured at BN = 224: 1.35 us per block with 2 + 2 stages, 1.16 us with 3 + 2,
+  // against 0.67 us of tensor time.  As many stages as 220 KiB hold, at most 4 + 4.
   static constexpr int TOTAL = 225280 / STAGE;
   static constexpr int NLO = TOTAL >= 8 ? 4 : TOTAL >= 6 ? 3 : 2;
   static constexpr int NRAW = (TOTAL - NLO) < 4 ? (TOTAL - NLO) : 4;
@@ -380,12 +380,11 @@ bool cached_map(CUtensorMap* out, const float* base, bool mn, int64_t R, int64_t
 }
 
 // CTA pairs (cta_group::2) for the K-major x K-major GEMMs: opt-in with PGNN_PAIR=1.  Measured on B200 (tools/check_tc.py,
-// tools/trace_tc.py): numerically identical to the single-CTA kernel, but a 32-deep block costs 1.05-1.08 us whatever the tile
-// width (BN = 224 and 128 alike, also for a lone cluster on an idle GPU, with or without the proxy fence / cluster-scope
-// wait), i.e. ~90 ns per UTCHMMA.2CTA with K = 8, against 1.05 us (BN 224) / 0.79 us (BN 128) for the single-CTA kernel with
-// the same ring depths.  GEMM1 31.0 vs 27.6 us, GEMM2 38.7 vs 29.2 us.  Kept as the starting point for a wider-K variant.
-// (An earlier 2-CTA variant that only TMA-multicast the B tile into both CTAs also measured no gain: at cluster size 2 the L2
-// already deduplicates the pair's requests.)
+// tools/trace_tc.py): numerically identical to the single-CTA kernel, but a 32-deep block costs 1.14-1.17 us whatever the tile
+// width (BN = 224 and 128 alike, 1.0 us for a lone cluster on an idle GPU, with or without the proxy fence / cluster-scope
+// wait), i.e. ~95 ns per UTCHMMA.2CTA with K = 8, against 1.16 us (BN 224) / 0.83 us (BN 128) for the single-CTA kernel.
+// GEMM1 31.0 vs 27.6 us, GEMM2 38.7 vs 29.2 us.  Kept as the starting point for round 2.
+// (An earlier 2-CTA variant that only TMA-multicast the B tile into both CTAs also measured no gain.)
 bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
