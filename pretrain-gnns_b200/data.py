@@ -1,4 +1,5 @@
-"""Device-resident molecule store and on-device batch collation.
+"""Device-resident molecule store and on-device batch collation, and the staging of
+host-collated batches (one pinned buffer, one asynchronous copy per batch) for callers that keep the reference's DataLoader.
 
 The reference collates on the host, one Python loop of `torch.cat`s per batch (chem/batch.py:17-52 BatchMasking,
 :141-210 BatchSubstructContext) inside DataLoader workers, then copies the batch to the GPU.  A B200 has 180 GB of
@@ -75,3 +76,94 @@ class MoleculeStore:
                                     out.edge_off.data_ptr(), out.x.data_ptr(), out.edge_index.data_ptr(), out.edge_attr.data_ptr(),
                                     out.batch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pgnn_collate_chem")
         return out
+
+
+class PackedHostBatch:
+    """A batch dict packed into ONE pinned host buffer (fields 16-byte aligned), built once per batch by BatchStager.pack."""
+
+    def __init__(self, buf, fields):
+        self.buf, self.fields = buf, fields  # fields: name -> (byte offset, byte length, dtype, shape)
+        self.nbytes = int(buf.numel())
+
+
+class BatchStager:
+    """Host -> device staging of batches with the copy off the critical path.
+
+    The reference moves a batch with one `.to(device)` per tensor right before the step (chem/pretrain_masking.py:47,
+    `batch = batch.to(device)`), i.e. five small synchronous-looking copies in front of the first kernel.  Here a batch is ONE
+    pinned buffer and ONE `cudaMemcpyAsync` on a side stream into one of `slots` device buffers, so the copy of batch i+1 runs
+    under the kernels of batch i:
+
+        t = stager.submit(packed[0])
+        for i in range(steps):
+            b = stager.take(t)                       # dict of device views; the compute stream waits for the copy
+            loss = train_step(b)                      # enqueue the step
+            t = stager.submit(packed[i + 1])         # prefetch under the step just enqueued
+            log(loss.item())
+
+    A slot is overwritten only after the work enqueued on the batch that last occupied it (everything up to the following
+    `take`) has finished: the side stream waits on an event of the compute stream, so no host synchronisation is assumed."""
+
+    def __init__(self, device, slots=2):
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.slots = int(slots)
+        self.dev = [None] * self.slots          # device buffers, grown on demand
+        self.ready = [None] * self.slots        # copy finished (side stream)
+        self.release = [None] * self.slots      # consumers enqueued (compute stream)
+        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self._next, self._last_taken = 0, None
+
+    def pack(self, batch):
+        fields, off = {}, 0
+        for k, v in batch.items():
+            if not torch.is_tensor(v):
+                continue
+            v = v.contiguous()
+            nb = v.numel() * v.element_size()
+            fields[k] = (off, nb, v.dtype, tuple(v.shape), v)
+            off = (off + nb + 15) // 16 * 16
+        buf = torch.empty(max(off, 16), dtype=torch.uint8)
+        if self.cuda:
+            buf = buf.pin_memory()
+        out = {}
+        for k, (o, nb, dt, shape, v) in fields.items():
+            if nb:
+                buf[o:o + nb].copy_(v.view(-1).view(torch.uint8))
+            out[k] = (o, nb, dt, shape)
+        return PackedHostBatch(buf, out)
+
+    def submit(self, packed):
+        """Start copying `packed` into the next slot; returns a ticket for take()."""
+        s = self._next
+        self._next = (s + 1) % self.slots
+        if self.dev[s] is None or self.dev[s].numel() < packed.nbytes:
+            self.dev[s] = torch.empty(max(packed.nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        if self.cuda:
+            if s == self._last_taken:  # the slot's batch is still the one in use: everything enqueued so far must finish first
+                self.release[s] = torch.cuda.Event()
+                self.release[s].record(torch.cuda.current_stream(self.device))
+                self._last_taken = None
+            if self.release[s] is not None:
+                self.stream.wait_event(self.release[s])
+            with torch.cuda.stream(self.stream):
+                self.dev[s][:packed.nbytes].copy_(packed.buf, non_blocking=True)
+                self.ready[s] = torch.cuda.Event()
+                self.ready[s].record(self.stream)
+        else:
+            self.dev[s][:packed.nbytes].copy_(packed.buf)
+        return (s, packed)
+
+    def take(self, ticket):
+        """-> dict of device tensors (views of the slot).  Everything enqueued on the previous batch is now 'released'."""
+        s, packed = ticket
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            if self._last_taken is not None and self._last_taken != s:
+                self.release[self._last_taken] = torch.cuda.Event()
+                self.release[self._last_taken].record(cur)
+            cur.wait_event(self.ready[s])
+        self._last_taken = s
+        d = self.dev[s]
+        return {k: (d[o:o + nb].view(dt).view(shape) if nb else torch.empty(shape, dtype=dt, device=self.device))
+                for k, (o, nb, dt, shape) in packed.fields.items()}

@@ -83,3 +83,23 @@ def test_adam_ctor_errors_match_torch():
         optim.Adam([])
     with pytest.raises(ValueError):
         optim.Adam([torch.nn.Parameter(torch.zeros(3))])  # CPU parameter: no fallback
+
+
+def test_batch_stager_roundtrip_cpu():
+    """Packing into one buffer, slot rotation and the views handed out (the CUDA side adds streams and events only)."""
+    st = data.BatchStager("cpu")
+    batches = []
+    for seed in range(5):
+        b = syn.mask_atoms(syn.zinc_batch(3 + seed, seed), seed)
+        b = {k: v for k, v in b.items() if torch.is_tensor(v)}
+        b["weights"] = torch.randn(7, 3)              # a second dtype and an odd byte length
+        b["empty"] = torch.zeros(0, 2, dtype=torch.int64)
+        batches.append(b)
+    packed = [st.pack(b) for b in batches]
+    assert all(p.nbytes % 16 == 0 or p.nbytes == 16 for p in packed)
+    ticket = st.submit(packed[0])
+    for i in range(5):
+        got = st.take(ticket)
+        ticket = st.submit(packed[(i + 1) % 5])      # prefetch: must not disturb the batch in use
+        for k, v in batches[i].items():
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape and torch.equal(got[k], v), (i, k)
