@@ -139,6 +139,8 @@ class BatchStager:
         self._next = (s + 1) % self.slots
         if self.dev[s] is None or self.dev[s].numel() < packed.nbytes:
             self.dev[s] = torch.empty(max(packed.nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+            if self.cuda:  # the allocator may hand back a block whose previous user is still running on the compute stream
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
         if self.cuda:
             if s == self._last_taken:  # the slot's batch is still the one in use: everything enqueued so far must finish first
                 self.release[s] = torch.cuda.Event()
