@@ -35,6 +35,7 @@ BATCH = 256
 NUM_LAYER, EMB = 5, 300
 NUM_DISTINCT_BATCHES = 8
 METRIC = "graphs/sec 5-layer GIN-300 fwd+bwd on ZINC-shaped batches"
+GATHER_DRAM_BYTES_NCU = 7281664  # k_aggregate_bwd, one `ncu --set full` capture (profiles/r01_mid_kernels_ncu.md)
 GEMM1_DRAM_BYTES_NCU = 7956992  # dram__bytes_read.sum + dram__bytes_write.sum of the B=256 GEMM1 launch (profiles/r01_gemm_tma_ncu.md)
 
 
@@ -460,7 +461,10 @@ def kernel_rooflines(ops, cabi, b, dev):
                     "ceiling of this scheme is peak/6 = %.0f TFLOP/s (achieved/ceiling = %.3f)" % (pk["tensor"] / 6, ach / (pk["tensor"] / 6)),
             "us_per_launch": t_gemm * 1e3}
     roof_g = {"bound": "hbm", "kernel": "k_aggregate_fwd (gather + segment sum, one layer pass)", "achieved": gbytes / (t_gather * 1e-3) / 1e9,
-              "peak": pk["hbm"], "unit": "GB/s", "frac": gbytes / (t_gather * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+              "peak": pk["hbm"], "unit": "GB/s", "frac": gbytes / (t_gather * 1e-3) / 1e9 / pk["hbm"],
+              # dram__bytes_read + write of the transpose-graph twin k_aggregate_bwd at these shapes (profiles/r01_mid_kernels_ncu.md):
+              # the matrix crosses DRAM once (7.28 MB) and the (E+N) row reads are served by L2 (39.4 MB of lts sectors)
+              "traffic": GATHER_DRAM_BYTES_NCU,
               "peak_source": pk["src"], "us_per_launch": t_gather * 1e3, "algorithmic_bytes": gbytes}
     return roof, roof_g
 
