@@ -26,13 +26,13 @@ def scatter_mean(src, index, dim=-1, out=None, dim_size=None, fill_value=0):
     return total / cnt.view(view)
 
 
-def scatter_max(src, index, dim=0, out=None, dim_size=None, fill_value=None):
+def scatter_max(src, index, dim=0, out=None, dim_size=None, fill_value=0):
+    """1.1.2: the output is created with `fill_value` (default 0, not -inf) and the maximum is taken INTO it, so the
+    result is max(fill_value, segment max) — a segment whose entries are all negative reports 0."""
     dim = dim % src.dim()
     assert dim == 0
     shape = _out_shape(src, dim, dim_size, index)
-    res = src.new_full(shape, float("-inf"))
+    res = src.new_full(shape, float("-inf") if fill_value is None else fill_value)
     idx = index.view([-1] + [1] * (src.dim() - 1)).expand_as(src)
     res = res.scatter_reduce(0, idx, src, reduce="amax", include_self=True)
-    if fill_value is not None:
-        res = torch.where(torch.isinf(res) & (res < 0), torch.full_like(res, fill_value), res)
     return res, None

@@ -108,8 +108,10 @@ k_gat_fwd(const float* __restrict__ xl, int64_t n, int H, int D, const float* __
     for (int j = 0; j < kJ; ++j) oacc[j] = 0.f;
     for (int h = 0; h < H; ++h) {
       const float pi = pq[(i * H + h) * 2];
-      // pass 1: segment max of the activated logits (lanes over messages; message hi is the self-loop)
-      float mx = -INFINITY;
+      // pass 1: segment max of the activated logits (lanes over messages; message hi is the self-loop).  The shift starts
+      // from 0, not -inf: torch_geometric 1.0.3's softmax subtracts torch_scatter 1.1.2's scatter_max, whose output is
+      // initialised with its default fill_value = 0, i.e. max(0, segment max) (chem/model.py:157).
+      float mx = 0.f;
       for (int k = lo + lane; k <= hi; k += 32) {
         const int s = k < hi ? nbr[k] : (int)i;
         float f[kQ];

@@ -165,3 +165,18 @@ def split_graphs(batch: dict):
     owner = np.searchsorted(ptr, ei[0], side="right") - 1  # edges are emitted graph by graph
     eptr = np.searchsorted(owner, np.arange(len(ptr)))
     return [(x[ptr[g]:ptr[g + 1]], ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]]) for g in range(len(ptr) - 1)]
+
+
+def one_direction_only(batch: dict, seed: int, keys=("edge_index", "edge_attr")) -> dict:
+    """Asymmetric variant of a batch: of every bond's two adjacent directed edges (u,v),(v,u) keep exactly one, chosen at
+    random.  The reference never feeds such a graph (chem/loader.py:83-86 always emits both directions), but only on it
+    does a swapped target/source — aggregation onto edge_index[1] instead of edge_index[0] — change GIN/GCN/GraphSAGE
+    results; the parity tests use it to pin the direction convention of every kernel."""
+    rng = np.random.default_rng(seed + 15485863)
+    out = dict(batch)
+    ei = batch[keys[0]]
+    m = ei.shape[1] // 2
+    keep = _t(2 * np.arange(m) + rng.integers(0, 2, size=m))
+    out[keys[0]] = ei[:, keep].contiguous()
+    out[keys[1]] = batch[keys[1]][keep].contiguous()
+    return out

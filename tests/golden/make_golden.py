@@ -39,13 +39,9 @@ CASES = {"chem": dict(graphs=4, data_seed=11, param_seed=5), "bio": dict(graphs=
 
 
 def load_reference_model(domain):
-    for m in ("model", "loader", "dataloader", "batch", "util"):
-        sys.modules.pop(m, None)
-    sys.path.insert(0, os.path.join(REF, domain))
-    try:
-        return importlib.import_module("model")
-    finally:
-        sys.path.pop(0)
+    from oracle import reference_runner
+    assert reference_runner.root() == REF, "goldens are generated from /root/reference itself, not from a staged copy"
+    return reference_runner.load(domain)
 
 
 def golden_batch(domain):

@@ -1,0 +1,126 @@
+"""CPU: the oracle restatement against the reference's OWN model.py / batch.py executed here (oracle/reference_runner.py:
+/root/reference in the build container, the staged git-ignored copy under oracle/_ref elsewhere; skipped when neither
+exists).  Unlike the frozen goldens this runs on fresh inputs each time it is asked to: symmetric AND one-direction-only
+graphs (the direction convention), every conv type, both domains, heads, and the batch collators."""
+import importlib
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn_oracle as O
+from oracle import reference_runner as R
+from oracle import step_io_oracle as SO
+
+syn = importlib.import_module("pretrain-gnns_b200.synthetic")
+pytestmark = pytest.mark.skipif(not R.available(), reason="reference sources not available (no /root/reference, no oracle/_ref)")
+TYPES = ("gin", "gcn", "graphsage", "gat")
+
+
+def _ref_step(mod, P, b, t, domain, training, dtype=torch.float32):
+    model = mod.GNN(5, 300, JK="last", drop_ratio=0, gnn_type=t)
+    assert str(model.load_state_dict(P)) == "<All keys matched successfully>"
+    model.to(dtype).train(training)
+    x = b["x"].to(dtype) if b["x"].is_floating_point() else b["x"]
+    ea = b["edge_attr"].to(dtype) if b["edge_attr"].is_floating_point() else b["edge_attr"]
+    return model, model(x, b["edge_index"], ea)
+
+
+def _batch(domain, directed, seed):
+    b = syn.zinc_batch(6, seed) if domain == "chem" else syn.ppi_batch(2, seed, n_lo=30, n_hi=50, num_tasks=8)
+    return syn.one_direction_only(b, seed) if directed else b
+
+
+@pytest.mark.parametrize("directed", [False, True])
+@pytest.mark.parametrize("domain", ["chem", "bio"])
+@pytest.mark.parametrize("t", TYPES)
+def test_oracle_equals_reference_fwd_bwd(domain, t, directed):
+    torch.set_num_threads(1)
+    mod = R.load(domain)
+    b = _batch(domain, directed, 31)
+    P = O.make_params(domain, t, 5, 300, seed=8)
+    fwd = O.chem_gnn if domain == "chem" else O.bio_gnn
+    with torch.no_grad():
+        _, ref_eval = _ref_step(mod, P, b, t, domain, False)
+        mine_eval = fwd(P, b["x"], b["edge_index"], b["edge_attr"], 5, t, False)
+    assert torch.allclose(mine_eval, ref_eval, atol=2e-6, rtol=2e-6), (mine_eval - ref_eval).abs().max()
+    # train-mode forward + backward, float64 on both sides: the two formulations must agree to rounding
+    Rm = torch.randn(ref_eval.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    model, y = _ref_step(mod, P, b, t, domain, True, torch.float64)
+    (y * Rm).sum().backward()
+    L = O.leaf_params(P, torch.float64)
+    x = b["x"].double() if b["x"].is_floating_point() else b["x"]
+    ea = b["edge_attr"].double() if b["edge_attr"].is_floating_point() else b["edge_attr"]
+    stats = {}
+    y2 = fwd(L, x, b["edge_index"], ea, 5, t, True, stats)
+    (y2 * Rm).sum().backward()
+    assert torch.allclose(y2, y, atol=1e-10, rtol=1e-9)
+    # per-tensor scale; a conv bias in front of BatchNorm has an exactly-zero gradient (pure rounding noise on both sides),
+    # so the scale is floored at 1e-4 of the model's largest gradient
+    gmax = max(float(p.grad.abs().max()) for p in model.parameters())
+    for k, p in model.named_parameters():
+        scale = max(float(p.grad.abs().max()), 1e-4 * gmax)
+        assert float((L[k].grad - p.grad).abs().max()) <= 1e-9 * scale, k
+    sd = model.state_dict()
+    for k, v in stats.items():
+        assert torch.allclose(v.double(), sd[k].double(), atol=1e-12, rtol=1e-10), k
+
+
+def test_direction_convention_is_visible_on_one_direction_graphs():
+    """On the reference's symmetric inputs a swapped target/source is invisible for GIN; on the
+    one-direction-only graphs used by the parity tests it is not — so those tests do pin the convention."""
+    mod = R.load("chem")
+    P = O.make_params("chem", "gin", 5, 300, seed=8)
+    for directed, differs in ((False, False), (True, True)):
+        b = _batch("chem", directed, 31)
+        with torch.no_grad():
+            _, ref = _ref_step(mod, P, b, "gin", "chem", False)
+            flipped = O.chem_gnn(P, b["x"], b["edge_index"].flip(0), b["edge_attr"], 5, "gin", False)
+        assert (not torch.allclose(flipped, ref, atol=1e-3)) == differs
+
+
+def test_graphpred_heads_equal_reference():
+    """chem/model.py:358-369 and bio/model.py:338-347 (mean pooling, centre-node concat, Linear)."""
+    g = torch.Generator().manual_seed(5)
+    for domain, T in (("chem", 12), ("bio", 40)):
+        mod = R.load(domain)
+        b = _batch(domain, False, 17)
+        P = O.make_params(domain, "gin", 5, 300, seed=2)
+        full = {"gnn." + k: v for k, v in P.items()}
+        width = 300 if domain == "chem" else 600
+        full["graph_pred_linear.weight"] = torch.randn(T, width, generator=g) * 0.05
+        full["graph_pred_linear.bias"] = torch.randn(T, generator=g) * 0.05
+        model = mod.GNN_graphpred(5, 300, T, JK="last", drop_ratio=0, graph_pooling="mean", gnn_type="gin")
+        assert str(model.load_state_dict(full)) == "<All keys matched successfully>"
+        model.eval()
+        with torch.no_grad():
+            if domain == "chem":
+                ref = model(b["x"], b["edge_index"], b["edge_attr"], b["batch"])
+                mine = O.chem_graphpred(full, b["x"], b["edge_index"], b["edge_attr"], b["batch"], b["num_graphs"], 5, "gin", False)
+            else:
+                data = types.SimpleNamespace(**{k: b[k] for k in ("x", "edge_index", "edge_attr", "batch", "center_node_idx")})
+                ref = model(data)
+                mine = O.bio_graphpred(full, b["x"], b["edge_index"], b["edge_attr"], b["batch"], b["center_node_idx"], b["num_graphs"], 5, "gin", False)
+        assert torch.allclose(mine, ref, atol=2e-6, rtol=2e-6)
+
+
+def test_collate_oracle_equals_reference_batch_masking():
+    """oracle/step_io_oracle.collate_chem against BatchMasking.from_data_list itself (chem/batch.py:17-52), fed
+    per-molecule Data objects that carry MaskAtom's extra keys."""
+    batch_mod = R.load("chem", "batch")
+    from torch_geometric.data import Data  # the stand-in (oracle/pyg103_standin)
+    b = syn.zinc_batch(9, 23)
+    graphs = syn.split_graphs(b)
+    ids = [3, 0, 8, 8, 5]
+    datas = []
+    for g in ids:
+        x, ei, ea = graphs[g]
+        datas.append(Data(x=torch.from_numpy(x.copy()), edge_index=torch.from_numpy(ei.copy()), edge_attr=torch.from_numpy(ea.copy()),
+                          masked_atom_indices=torch.tensor([0, x.shape[0] - 1])))
+    ref = batch_mod.BatchMasking.from_data_list(datas)
+    mine = SO.collate_chem(graphs, ids)
+    for k in ("x", "edge_index", "edge_attr", "batch"):
+        assert np.array_equal(mine[k], ref[k].numpy()), k
+    exp_masked = np.concatenate([np.array([0, graphs[g][0].shape[0] - 1]) + mine["node_off"][i] for i, g in enumerate(ids)])
+    assert np.array_equal(exp_masked, ref.masked_atom_indices.numpy())
