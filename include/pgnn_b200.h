@@ -233,6 +233,17 @@ PGNN_API int pgnn_shifted_rowdot_fwd(const float* a, int64_t lda, const float* b
 PGNN_API int pgnn_shifted_rowdot_bwd(const float* g, const float* a, int64_t lda, const float* b, int64_t ldb,
                                      int64_t B, int64_t C, int64_t shift, int accumulate,
                                      float* ga, int64_t ldga, float* gb, int64_t ldgb, void* stream);
+/* Mean binary cross-entropy with logits over fp32 logits [M,N] evaluated in fp64 (BCEWithLogitsLoss on pred.double()):
+ *   target_kind 0: every target = const_target         (chem/pretrain_contextpred.py:86-87: ones for pred_pos, zeros for pred_neg)
+ *   target_kind 1: target int64 [M, ldt] in {0,1}      (bio/pretrain_supervised.py:33-36: go_target_pretrain)
+ *   target_kind 2: target int64 in {-1,0,+1}; 0 = missing label, dropped; the rest use (y+1)/2; loss = sum / #valid
+ *                                                      (chem/finetune.py:33-43)
+ * *loss_mean (device fp64 scalar) is OVERWRITTEN; dlogits [M, lddl] receives d loss / d logits (0 at dropped entries).
+ * Deterministic (no floating-point atomics).  workspace: pgnn_bce_logits_workspace_bytes() bytes, any content. */
+PGNN_API int64_t pgnn_bce_logits_workspace_bytes(void);
+PGNN_API int pgnn_bce_logits_fwd(const float* logits, int64_t ld, int64_t M, int64_t N, const int64_t* target, int64_t ldt,
+                                 int target_kind, double const_target, double* loss_mean, float* dlogits, int64_t lddl,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Whole-encoder entry points: chem GNN with gnn_type="gin", JK="last", drop_ratio=0 (chem/model.py:255-290).

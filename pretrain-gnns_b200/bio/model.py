@@ -174,6 +174,7 @@ class GNN_graphpred(nn.Module):
 
     def forward(self, data):
         rep = self.gnn(data.x, data.edge_index, data.edge_attr)
-        pooled = self.pool(rep, data.batch)
+        # one centre node per graph (bio/batch.py:39-40): the segment count is known without reading batch.max() back
+        pooled = self.pool(rep, data.batch, int(data.center_node_idx.shape[0]))
         center = ops.row_gather(rep, data.center_node_idx)
         return ops.linear(torch.cat([pooled, center], dim=1), self.graph_pred_linear.weight, self.graph_pred_linear.bias)

@@ -513,6 +513,54 @@ def shifted_rowdot(a, b, shift=0):
     return _ShiftedRowDot.apply(a, b, int(shift))
 
 
+class _BceLogits(Function):
+    @staticmethod
+    def forward(ctx, logits, target, kind, const):
+        _dev(logits, target)
+        x = _f32(logits)
+        x2 = x.reshape(1, -1) if x.dim() == 1 else x
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M, N = x2.shape
+        t = None
+        if kind != 0:
+            t = target.reshape(M, N).contiguous()
+            if t.dtype != torch.int64:
+                raise PgnnError("BCE targets must be int64 ({0,1}, or {-1,0,+1} for the masked form)")
+        dev = x.device
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        dl = torch.empty(M, N, dtype=torch.float32, device=dev)
+        wsb = lib.pgnn_bce_logits_workspace_bytes()
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.pgnn_bce_logits_fwd(_p(x2), x2.stride(0) if M > 1 else max(N, 1), M, N, _p(t), N, int(kind), float(const), _p(loss),
+                                      _p(dl), max(N, 1), _p(ws), wsb, _st()), "bce_logits_fwd")
+        ctx.save_for_backward(dl)
+        ctx.shape = tuple(logits.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g.to(torch.float32)).view(ctx.shape), None, None, None
+
+
+def bce_with_logits(logits, target):
+    """`nn.BCEWithLogitsLoss()(logits.double(), target.double())` (bio/pretrain_supervised.py:33-36): mean over all entries,
+    evaluated in fp64; target int64 in {0,1}, same shape as logits.  Returns an fp64 scalar."""
+    return _BceLogits.apply(logits, target, 1, 0.0)
+
+
+def bce_with_logits_const(logits, target_value):
+    """Same against a constant target (chem/pretrain_contextpred.py:86-87: ones for the positive, zeros for the negative scores)."""
+    return _BceLogits.apply(logits, None, 0, float(target_value))
+
+
+def masked_bce_with_logits(logits, y):
+    """chem/finetune.py:33-43: y in {-1,0,+1}, entries with y == 0 carry no label; BCE on (y+1)/2 summed over the valid entries
+    and divided by their number."""
+    return _BceLogits.apply(logits, y, 2, 0.0)
+
+
 class _Gat(Function):
     @staticmethod
     def forward(ctx, xl, att, T, bias, edge_attr, graph, heads, slope, is_bio):
@@ -657,23 +705,25 @@ def _pad4(n):
 
 class _MaskedCE(Function):
     @staticmethod
-    def forward(ctx, node_rep, idx, labels, weight, bias):
-        _dev(node_rep, idx, labels, weight, bias)
+    def forward(ctx, node_rep, idx, labels, weight, bias, idx2=None):
+        _dev(node_rep, idx, labels, weight, bias, idx2)
         rep, w = _f32(node_rep), _f32(weight).contiguous()
         idx, labels = idx.contiguous(), labels.contiguous()
-        if idx.dtype != torch.int64 or labels.dtype != torch.int64:
+        idx2 = None if idx2 is None else idx2.contiguous()
+        if idx.dtype != torch.int64 or labels.dtype != torch.int64 or (idx2 is not None and idx2.dtype != torch.int64):
             raise PgnnError("indices and labels must be int64")
         M, D, V = idx.shape[0], rep.shape[1], w.shape[0]
         ldv = _pad4(V)  # 16-byte aligned logit rows: the TMA boxes of the backward GEMMs zero-fill the ragged class extent
         dev = rep.device
         rows = torch.empty(M, D, dtype=torch.float32, device=dev)
-        check(lib.pgnn_row_gather_fwd(_p(rep), rep.stride(0), _p(idx), None, M, D, _p(rows), D, _st()), "row_gather_fwd")
+        check(lib.pgnn_row_gather_fwd(_p(rep), rep.stride(0), _p(idx), _p(idx2), M, D, _p(rows), D, _st()), "row_gather_fwd")
         logits = torch.empty(M, ldv, dtype=torch.float32, device=dev)
         check(lib.pgnn_linear_fwd(_p(rows), D, _p(w), _p(bias), M, V, D, 0, _p(logits), ldv, _precision, _st()), "linear_fwd")
         loss = torch.empty((), dtype=torch.float64, device=dev)
         dlogits = torch.empty(M, ldv, dtype=torch.float32, device=dev)
         check(lib.pgnn_softmax_ce_fwd(_p(logits), ldv, M, V, _p(labels), _p(loss), _p(dlogits), ldv, _st()), "softmax_ce_fwd")
         ctx.save_for_backward(rows, dlogits, w, idx)
+        ctx.idx2 = idx2
         ctx.dims = (tuple(rep.shape), M, D, V, ldv, bias is not None)
         ctx.logits = logits[:, :V]
         ctx.mark_non_differentiable(ctx.logits)
@@ -693,8 +743,8 @@ class _MaskedCE(Function):
             drows = torch.empty(M, D, dtype=torch.float32, device=dev)
             check(lib.pgnn_linear_bwd_x(_p(dl), ldv, _p(w), M, V, D, None, 0, _p(drows), D, _precision, _st()), "linear_bwd_x")
             grep = torch.zeros(n, D, dtype=torch.float32, device=dev)
-            check(lib.pgnn_row_gather_bwd(_p(drows), D, _p(idx), None, M, D, _p(grep), D, _st()), "row_gather_bwd")
-        return grep, None, None, gw, gb
+            check(lib.pgnn_row_gather_bwd(_p(drows), D, _p(idx), _p(ctx.idx2), M, D, _p(grep), D, _st()), "row_gather_bwd")
+        return grep, None, None, gw, gb, None
 
 
 def masked_atom_loss(node_rep, masked_atom_indices, labels, weight, bias=None):
@@ -702,3 +752,10 @@ def masked_atom_loss(node_rep, masked_atom_indices, labels, weight, bias=None):
     nn.CrossEntropyLoss (mean): gather, Linear(emb_dim, V), softmax cross-entropy evaluated in fp64.
     Returns (loss: fp64 scalar tensor, logits: [M, V] fp32, non-differentiable — e.g. for compute_accuracy)."""
     return _MaskedCE.apply(node_rep, masked_atom_indices, labels, weight, bias)
+
+
+def masked_bond_loss(node_rep, edge_index, connected_edge_indices, labels, weight, bias=None):
+    """chem/pretrain_masking.py:57-61: `edge_rep = node_rep[u] + node_rep[v]` for the masked bonds
+    `edge_index[:, connected_edge_indices]`, `Linear(emb_dim, 4)`, mean CE on fp64 logits.  -> (loss fp64, logits [M, 4])."""
+    me = edge_index.index_select(1, connected_edge_indices)
+    return _MaskedCE.apply(node_rep, me[0], labels, weight, bias, me[1])

@@ -134,3 +134,69 @@ def grad_close(mine, ref32, ref64, floor=1.0, gtol=2e-4, slack=4.0):
     tol = max(gtol, slack * e_ref)
     ok, e = close_scaled(mine, ref64, tol, floor)
     return ok, e, tol
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Full-size oracle parity (tests/test_gpu_parity_full.py): per-tensor bounds stated against what is measured.
+#
+# Forward outputs: the north_star bound |mine - ref32| <= 1e-4 + 1e-4 |ref32|, AND max|mine - ref64| <= OUT_REL x the
+# tensor's largest magnitude (measured on B200: 1-4e-6 for the 3xTF32 path; OUT_REL is ~10x that).
+# Gradients, per tensor: err = max|mine - ref64| / scale with scale = the tensor's own largest |ref64| (floored at 1e-3 of the
+# model's largest gradient; a structurally zero gradient -- a bias in front of train-mode BatchNorm -- is compared on the
+# model's scale).  Train-mode BatchNorm makes fp32 gradients ill-conditioned: the oracle's OWN fp32 run misses its fp64 run
+# by e_ref (up to ~1e-3 of scale at B=256), so the bound is  err <= max(GRAD_REL, SLACK x e_ref)  (measured: err <= ~1.5 e_ref).
+# ReLU-boundary allowance (relative Frobenius error <= 5e-3) ONLY when the fp64 oracle run actually has a ReLU
+# pre-activation within rounding distance of zero (oracle.gnn_oracle.near_zero_preactivations), and it is reported.
+# ---------------------------------------------------------------------------------------------------------------------
+OUT_REL = 4e-5
+GRAD_REL = 5e-5
+SLACK = 3.0
+
+
+def output_check(name, mine, ref32, ref64, rows):
+    mine, ref32, ref64 = (torch.as_tensor(t).detach().cpu().double() for t in (mine, ref32, ref64))
+    scale = max(float(ref64.abs().max()), 1e-30)
+    e64 = float((mine - ref64).abs().max()) / scale
+    eref = float((ref32 - ref64).abs().max()) / scale
+    north = bool(((mine - ref32).abs() <= 1e-4 + 1e-4 * ref32.abs()).all())
+    ok = north and e64 <= max(OUT_REL, SLACK * eref)
+    rows.append(dict(kind="out", name=name, err=e64, err_ref32=eref, north_star=north, ok=ok))
+    return ok
+
+
+def gradient_check(named_mine, g32, g64, near_zero, rows):
+    gmax = max(float(v.abs().max()) for v in g64.values())
+    ok_all = True
+    for k, mine in named_mine:
+        mine = mine.detach().cpu().double()
+        r64, r32 = g64[k].double(), g32[k].double()
+        tmax = float(r64.abs().max())
+        zero = tmax < 1e-9 * gmax
+        scale = gmax if zero else max(tmax, 1e-3 * gmax)
+        e = float((mine - r64).abs().max()) / scale
+        eref = float((r32 - r64).abs().max()) / scale
+        tol = max(GRAD_REL, SLACK * eref)
+        ok, via = e <= tol, "max"
+        if not ok and near_zero > 0 and r64.numel() >= 64:
+            fro = float((mine - r64).norm() / max(float(r64.norm()), 1e-30))
+            if fro <= 5e-3:
+                ok, via = True, "relu-boundary allowance (fro %.2e, %d near-zero pre-activations)" % (fro, near_zero)
+        rows.append(dict(kind="grad", name=k, err=e, err_ref32=eref, tol=tol, ok=ok, via=via, structurally_zero=zero))
+        ok_all &= ok
+    return ok_all
+
+
+def write_report(test_name, rows, extra=None):
+    """Measured errors of a parity test -> gpurun_out/parity/<test>.json (travels back from the GPU box)."""
+    import json
+    d = os.path.join(os.path.dirname(HERE), "gpurun_out", "parity")
+    try:
+        os.makedirs(d, exist_ok=True)
+        worst = {}
+        for r in rows:
+            w = worst.setdefault(r["kind"], dict(err=0.0, err_ref32=0.0))
+            w["err"], w["err_ref32"] = max(w["err"], r["err"]), max(w["err_ref32"], r["err_ref32"])
+        with open(os.path.join(d, test_name + ".json"), "w") as fh:
+            json.dump(dict(test=test_name, worst=worst, extra=extra or {}, rows=rows), fh, indent=1)
+    except OSError:
+        pass

@@ -6,6 +6,8 @@ import sys
 
 import torch
 
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
@@ -22,8 +24,19 @@ def test_reference_arm_line():
     assert line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 1 and line["value"] > 0
     assert line["metric"].startswith("graphs/sec") and "workload" in line["config"] and line["data"] == "synthetic"
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    from oracle import reference_runner
+    assert cb["kind"] == ("reference" if reference_runner.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert set(line["config"]) == {"workload", "name", "global_batch", "per_gpu_batch", "parallelism", "optimizer_step", "l2"}
     assert line["e2e"] == {"value": line["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_configs():
+    for cfg in ("contextpred", "gat"):
+        r = _run("--impl", "reference", "--config", cfg, "--steps", "1", "--warmup", "1")
+        assert r.returncode == 0, r.stderr[-500:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line["config"]["name"] == cfg and line["value"] > 0 and cfg in line["metric"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

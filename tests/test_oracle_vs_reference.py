@@ -124,3 +124,38 @@ def test_collate_oracle_equals_reference_batch_masking():
         assert np.array_equal(mine[k], ref[k].numpy()), k
     exp_masked = np.concatenate([np.array([0, graphs[g][0].shape[0] - 1]) + mine["node_off"][i] for i, g in enumerate(ids)])
     assert np.array_equal(exp_masked, ref.masked_atom_indices.numpy())
+
+
+@pytest.mark.parametrize("config", ["masking", "contextpred", "bio_supervised", "gcn", "gat", "graphsage"])
+def test_train_bodies_port_equals_reference(config):
+    """oracle/steps_oracle.py: the restated train() bodies (loss + every gradient) against the same bodies on the
+    reference's own modules, at a small batch."""
+    from oracle import steps_oracle as S
+    torch.set_num_threads(1)
+    ts = importlib.import_module("pretrain-gnns_b200.train_steps")
+    T = 24
+    if config == "bio_supervised":
+        b = {k: v for k, v in syn.ppi_batch(3, 5, n_lo=30, n_hi=50, num_tasks=T).items() if k in ts.BioSupervisedStep.KEYS}
+    elif config == "contextpred":
+        b = {k: v for k, v in syn.substruct_context_batch(8, 5).items() if k in ts.ContextPredStep.KEYS}
+    else:
+        mb = syn.mask_atoms(syn.zinc_batch(8, 5), 5)
+        b = {k: mb[k] for k in ("x", "edge_index", "edge_attr", "masked_atom_indices")} | {"labels": mb["mask_node_label"][:, 0].contiguous()}
+    P = S.make_params(config, 3, num_tasks=T)
+    ref = S.REFERENCE_STEPS[config]() if config != "bio_supervised" else S.ReferenceBioSupervisedStep(T)
+    ref.load(P)
+    loss_ref = ref(b)
+    L = O.leaf_params(P)
+    loss, _ = S.LOSSES[config](L, b)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-6 * max(1.0, abs(float(loss_ref)))
+    named = {name + "." + k: p for name, m in ref.named.items() for k, p in m.named_parameters()}
+    gmax = max(float(p.grad.abs().max()) for p in named.values())
+    L64 = O.leaf_params(P, torch.float64)
+    S.LOSSES[config](L64, b)[0].backward()
+    for k, p in named.items():
+        # a bias in front of train-mode BatchNorm has a structurally zero gradient (fp64: ~1e-17): rounding noise on both sides
+        zero = float(L64[k].grad.abs().max()) < 1e-9 * gmax
+        scale = gmax if zero else max(float(p.grad.abs().max()), 1e-3 * gmax)
+        # same arithmetic in a different order (fp32): agreement to a few ulps of the accumulated magnitude
+        assert float((L[k].grad - p.grad).abs().max()) <= 2e-4 * scale, (k, float((L[k].grad - p.grad).abs().max()) / scale)
