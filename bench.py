@@ -17,12 +17,13 @@ rank) and the step includes ONE all-reduce of the gradients.
 One JSON line is printed by rank 0.  `value` times K steps with the batches already resident in HBM (graph bucketing
 included: every step sees a different batch).  `e2e` times the same K steps from pinned host memory: one packed pinned
 buffer and one asynchronous H2D copy per step inside the timed region (the next batch prefetched under the running step) and
-one D2H read of the loss per step (issued asynchronously after the step, consumed one step later, as the reference's
+one D2H read of the loss per step (issued asynchronously after the step, consumed two steps later, as the reference's
 `loss_accum += loss.item()` only feeds a log line).  L2 is flushed between timed steps (256 MiB memset outside the per-step
 event pairs).  `--impl reference` times the reference's OWN model.py on the host cores (oracle/reference_runner.py;
 kind "reference"), or the oracle port of it when the reference's sources are not on the box (kind "port").
 """
 import argparse
+import gc
 import importlib
 import json
 import os
@@ -346,8 +347,9 @@ def run_b200(args, rank, world, local_rank):
     stager = pdata.BatchStager(dev)
     packed = [stager.pack(b) for b in host]
     h2d_bytes = packed[0].nbytes
-    loss_host = torch.zeros(2, dtype=torch.float64).pin_memory()
-    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    LAG = 2  # the loss of step i is consumed while step i + LAG runs: the host may run up to LAG steps ahead of the GPU
+    loss_host = torch.zeros(LAG + 1, dtype=torch.float64).pin_memory()
+    loss_ready = [torch.cuda.Event() for _ in range(LAG + 1)]
 
     def timed(e2e):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -357,6 +359,8 @@ def run_b200(args, rank, world, local_rank):
             train_step(b).item()
         barrier()
         n0 = cabi.lib.pgnn_kernel_launch_count()
+        gc.collect()
+        gc.disable()  # a collection in the middle of the loop stalls the launch thread for milliseconds (seen as 2-9 ms steps)
         t0 = time.perf_counter()
         ticket, acc = None, 0.0
         for i in range(args.steps):
@@ -367,19 +371,24 @@ def run_b200(args, rank, world, local_rank):
                     ticket = stager.submit(packed[i % len(packed)])
                 loss = train_step(stager.take(ticket))
                 ticket = stager.submit(packed[(i + 1) % len(packed)]) if i + 1 < args.steps else None
-                loss_host[i & 1].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's loss
-                loss_ready[i & 1].record()
-                if i:  # consume the previous step's loss while this step runs
-                    loss_ready[(i - 1) & 1].synchronize()
-                    acc += float(loss_host[(i - 1) & 1])
+                slot = i % (LAG + 1)
+                loss_host[slot].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's loss
+                loss_ready[slot].record()
+                if i >= LAG:  # consume an earlier step's loss while this one runs
+                    j = (i - LAG) % (LAG + 1)
+                    loss_ready[j].synchronize()
+                    acc += float(loss_host[j])
             else:
                 train_step(resident[i % len(resident)])
             ev[i][1].record()
         if e2e:
-            loss_ready[(args.steps - 1) & 1].synchronize()
-            acc += float(loss_host[(args.steps - 1) & 1])
+            for i in range(max(args.steps - LAG, 0), args.steps):
+                j = i % (LAG + 1)
+                loss_ready[j].synchronize()
+                acc += float(loss_host[j])
         barrier()
         wall = time.perf_counter() - t0
+        gc.enable()
         launches = cabi.lib.pgnn_kernel_launch_count() - n0
         per = [a.elapsed_time(b) for a, b in ev]
         t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
@@ -418,12 +427,13 @@ def run_b200(args, rank, world, local_rank):
                                                             "--precision fp32 runs the exact FFMA kernels)" if ops.get_precision() != "fp32" else ""),
                    "grad_allreduce": (reducer.backend if reducer is not None else "none (1 GPU)"),
                    "per_step_ms": dist_stats(per_dev), "per_step_ms_e2e": dist_stats(per_e2e),
+                   "slowest_e2e_steps": sorted(((round(t, 3), i) for i, t in enumerate(per_e2e)), reverse=True)[:4],
                    "wall_ms_per_step_incl_flush": 1e3 * wall_dev / args.steps, "wall_ms_per_step_incl_flush_e2e": 1e3 * wall_e2e / args.steps,
                    "mean_loss_e2e": mean_loss, "gemm_flops_per_step": wm["gemm_flops_per_step"]},
         "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps,
                 "transport": "one pinned buffer + one async H2D copy per batch on a side stream, next batch prefetched under the step "
-                             "(data.BatchStager); loss copied to pinned memory after every step and consumed one step later"},
+                             "(data.BatchStager); loss copied to pinned memory after every step and consumed two steps later"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roof, "roofline_gather": roof_gather,

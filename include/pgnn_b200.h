@@ -32,6 +32,17 @@ extern "C" {
 #define PGNN_EWORKSPACE (-3)  /* workspace smaller than the *_workspace_bytes query */
 #define PGNN_EUNSUPPORTED (-4)
 
+/* Index preconditions.  Every index the kernels consume must be in range: node ids of edge_index and segment ids in
+ * [0, num_nodes / num_segments), atom codes in [0,120) x [0,3) (chem/model.py:9-10), bond codes in [0,6) x [0,3) (:12-13),
+ * class labels in [0, V), gather indices in [0, rows).  The reference's torch ops raise a device-side assert otherwise; here
+ * the consuming kernel drops / clamps the offending element (never reads or writes out of range) and ORs one of these bits
+ * into a per-device error word, which pgnn_device_error_flags() reads back (it synchronises the device). */
+#define PGNN_DEVERR_NODE_ID 1u     /* edge_index entry or segment id (graph_prep, bucket) */
+#define PGNN_DEVERR_ATOM_CODE 2u   /* chem x[:,0] / x[:,1] (chem_embed_*, chem_gin_*) */
+#define PGNN_DEVERR_BOND_CODE 4u   /* chem edge_attr (chem_edge_summary, gat) */
+#define PGNN_DEVERR_LABEL 8u       /* softmax_ce labels */
+#define PGNN_DEVERR_GATHER 16u     /* row_gather indices */
+
 /* reduction modes of the neighbour aggregation */
 #define PGNN_AGG_SUM 0   /* GIN:  chem/model.py:49,  bio/model.py:52            */
 #define PGNN_AGG_MEAN 1  /* SAGE: chem/model.py:169, bio/model.py:184 (count = in-degree + 1) */
@@ -39,7 +50,9 @@ extern "C" {
 
 PGNN_API int pgnn_version(void);
 PGNN_API const char* pgnn_error_string(int code);
-PGNN_API int pgnn_last_cuda_error(void);          /* cudaError_t of the last PGNN_ECUDA on this thread */
+PGNN_API int pgnn_last_cuda_error(void);
+/* Synchronise the current device and return its PGNN_DEVERR_* bits (>= 0; negative = error code); clear != 0 resets them. */
+PGNN_API int pgnn_device_error_flags(int clear);          /* cudaError_t of the last PGNN_ECUDA on this thread */
 PGNN_API int pgnn_device_sm_count(int device);   /* host query; negative on error */
 PGNN_API int64_t pgnn_kernel_launch_count(void); /* kernels this library has enqueued since load (process-wide) */
 /* Per-kernel timing mode: while enabled, every kernel launch of the library is bracketed by a CUDA event pair on its own
@@ -95,7 +108,7 @@ PGNN_API int pgnn_bio_edge_summary(const float* edge_attr /*[E,9]*/, const int32
  * Input embeddings.  chem/model.py:264  h0 = E1[x[:,0]] + E2[x[:,1]];  bio/model.py:49-50
  * h0 = E[(long) x] (one table, float-coded index).
  * ------------------------------------------------------------------------------------------- */
-PGNN_API int pgnn_chem_embed_fwd(const int64_t* x /*[N,2]*/, const float* tab1, const float* tab2,
+PGNN_API int pgnn_chem_embed_fwd(const int64_t* x /*[N,2]*/, const float* tab1, int64_t rows1, const float* tab2, int64_t rows2,
                                  int64_t num_nodes, int64_t C, float* out, int64_t ldo, void* stream);
 /* gtab1 [rows1,C], gtab2 [rows2,C] are OVERWRITTEN (zeroed, then accumulated) */
 PGNN_API int pgnn_chem_embed_bwd(const int64_t* x, const float* g, int64_t ldg, int64_t num_nodes, int64_t C,
@@ -216,11 +229,11 @@ PGNN_API int pgnn_segment_mean_fwd(const float* x, int64_t ldx, const int32_t* s
 PGNN_API int pgnn_segment_mean_bwd(const float* g, int64_t ldg, const int64_t* seg, const int32_t* seg_ptr,
                                    int64_t num_rows, int64_t C, float* gx, int64_t ldgx, void* stream);
 /* out[m,:] = x[idx[m],:] (+ x[idx2[m],:] if idx2 != NULL: the bond representation rep[u]+rep[v]) */
-PGNN_API int pgnn_row_gather_fwd(const float* x, int64_t ldx, const int64_t* idx, const int64_t* idx2,
+PGNN_API int pgnn_row_gather_fwd(const float* x, int64_t ldx, int64_t num_rows, const int64_t* idx, const int64_t* idx2,
                                  int64_t num_idx, int64_t C, float* out, int64_t ldo, void* stream);
 /* gx[idx[m],:] += g[m,:] (and idx2). gx must be pre-initialised by the caller (accumulates). */
 PGNN_API int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const int64_t* idx2,
-                                 int64_t num_idx, int64_t C, float* gx, int64_t ldgx, void* stream);
+                                 int64_t num_idx, int64_t C, float* gx, int64_t ldgx, int64_t num_rows, void* stream);
 /* Mean cross-entropy of fp32 logits [M,V] evaluated in fp64 (criterion(pred.double(), labels), chem/pretrain_masking.py:52).
  * *loss_mean (device fp64 scalar) is OVERWRITTEN; dlogits [M, lddl] receives (softmax - onehot)/M (columns V..lddl-1 zeroed),
  * i.e. the gradient of the loss w.r.t. the logits.  labels: int64 [M] in [0, V). */
@@ -272,6 +285,29 @@ PGNN_API int pgnn_chem_gin_backward(const void* const* params, const float* g_no
                                     int64_t N, int64_t E, int64_t L, int64_t D, int precision, float* grads,
                                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same two-call contract for gnn_type = "gcn" | "graphsage" | "gat" (chem/model.py:58-202 inside GNN.forward :255-290).
+ * params order: [x_embedding1.weight, x_embedding2.weight, then per layer
+ *   gcn / graphsage: gnns.l.linear.weight [D,D], .linear.bias, .edge_embedding1.weight [6,D], .edge_embedding2.weight [3,D],
+ *                    batch_norms.l.weight, .bias                                                         (6 per layer)
+ *   gat (heads = 2): gnns.l.weight_linear.weight [2D,D], .weight_linear.bias [2D], .att [1,2,2D], .bias [D],
+ *                    .edge_embedding1.weight [6,2D], .edge_embedding2.weight [3,2D], batch_norms.l.weight, .bias  (8 per layer)]
+ * The flat gradient buffer uses the same order (pgnn_chem_conv_grad_offsets).  backward also takes edge_attr (GAT re-reads the
+ * bond codes); everything else as for pgnn_chem_gin_*. */
+#define PGNN_CONV_GCN 1
+#define PGNN_CONV_SAGE 2
+#define PGNN_CONV_GAT 3
+PGNN_API int64_t pgnn_chem_conv_num_params(int conv_type, int64_t L);
+PGNN_API int pgnn_chem_conv_grad_offsets(int conv_type, int64_t L, int64_t D, int64_t* offsets);
+PGNN_API int64_t pgnn_chem_conv_workspace_bytes(int conv_type, int64_t N, int64_t E, int64_t L, int64_t D);
+PGNN_API int pgnn_chem_conv_forward(int conv_type, const void* const* params, void* const* bn_running_mean,
+                                    void* const* bn_running_var, void* const* bn_num_batches_tracked, const int64_t* x,
+                                    const int64_t* edge_index, const int64_t* edge_attr, int64_t N, int64_t E, int64_t L,
+                                    int64_t D, int training, float momentum, float eps, int precision, float* node_rep,
+                                    int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+PGNN_API int pgnn_chem_conv_backward(int conv_type, const void* const* params, const float* g_node_rep, int64_t ldg,
+                                     const int64_t* x, const int64_t* edge_attr, int64_t N, int64_t E, int64_t L, int64_t D,
+                                     int precision, float* grads, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Either side of the path inside a training step (f1 collation, f2 optimizer).
  * ------------------------------------------------------------------------------------------- */
@@ -289,6 +325,32 @@ PGNN_API int pgnn_collate_chem(const int64_t* node_ptr, const int64_t* edge_ptr,
                                const int32_t* store_edge_index, int64_t store_num_edges, const uint8_t* store_edge_attr,
                                const int64_t* graph_ids, int64_t B, int64_t* node_off, int64_t* edge_off, int64_t* x,
                                int64_t* edge_index, int64_t* edge_attr, int64_t* batch, void* stream);
+
+/* MaskAtom (chem/util.py:189-241, mask_edge=False) on a collated batch: per graph int(n * mask_rate + 1) distinct atoms (uniform
+ * k-subset: the k smallest splitmix64(seed, position-in-batch) keys of the graph), labels saved, x rows overwritten with
+ * [mask_token, 0] (mask_token = num_atom_type = 119, chem/pretrain_masking.py:122).  x [N,2] int64 is modified IN PLACE;
+ * node_off [B+1] as written by pgnn_collate_chem.  Outputs: mask_off [B+1] (exclusive scan of the sample sizes),
+ * masked_atom_indices [M] (batch-global node ids, ascending inside a graph), mask_node_label [M,2]; M =
+ * pgnn_mask_atoms_count(host copy of node_off, B, mask_rate).  Integer work, bit-exact against oracle/step_io_oracle.py.
+ * Not built: mask_edge=True (chem/util.py:243-272; off by default in pretrain_masking.py). */
+PGNN_API int64_t pgnn_mask_atoms_count(const int64_t* node_off_host, int64_t B, double mask_rate);
+PGNN_API int pgnn_mask_atoms(int64_t* x, const int64_t* node_off, int64_t B, double mask_rate, int64_t mask_token, int64_t seed,
+                             int64_t* mask_off, int64_t* masked_atom_indices, int64_t* mask_node_label, void* stream);
+/* Per-graph index lists of a batch (chem/batch.py:41-42,170-199; bio/batch.py:39-40): the store holds list_ptr [G+1] int64 and
+ * values int32 (graph-local node ids); for the selected graphs out[list_off[i] + j] = values[list_ptr[g_i] + j] +
+ * add_per_graph[i] (e.g. node_off of the same collation; NULL = 0), seg[...] = i (batch_overlapped_context; may be NULL),
+ * sizes[i] = list length (overlapped_context_size; may be NULL).  list_off [B+1] receives the exclusive scan. */
+PGNN_API int pgnn_collate_lists(const int64_t* list_ptr, const int32_t* values, const int64_t* graph_ids, int64_t B,
+                                const int64_t* add_per_graph, int64_t* list_off, int64_t* out, int64_t* seg, int64_t* sizes,
+                                void* stream);
+/* bio/batch.py:17-50 for a store of PPI ego graphs: node_ptr / edge_ptr [G+1], store_edge_index [2][Et] int32 graph-local,
+ * store_edge_bits [Et] uint16 = the 9 binary edge attributes of bio/loader.py:57-75 packed LSB-first.  Outputs: x float [N,1]
+ * (the constant dummy label 1.0, bio/loader.py:47), edge_index int64 [2,E] with the node offset added, edge_attr float [E,9],
+ * batch int64 [N], node_off / edge_off [B+1]. */
+PGNN_API int pgnn_collate_bio(const int64_t* node_ptr, const int64_t* edge_ptr, const int32_t* store_edge_index,
+                              int64_t store_num_edges, const uint16_t* store_edge_bits, const int64_t* graph_ids, int64_t B,
+                              int64_t* node_off, int64_t* edge_off, float* x, int64_t* edge_index, float* edge_attr,
+                              int64_t* batch, void* stream);
 
 /* Multi-tensor Adam: torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.decay).step()
  * (chem/pretrain_masking.py:134-136,72-74; chem/pretrain_contextpred.py:160-161,96-97) for every tensor in one launch.

@@ -59,6 +59,34 @@ def available():
     return root() is not None
 
 
+class _Placeholder:
+    """Stands for any name of an absent package: attribute access yields another placeholder (loader.py builds tables of
+    `Chem.rdchem.ChiralType.*` constants at import time), calling one raises."""
+
+    def __init__(self, path):
+        self._path = path
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Placeholder(self._path + "." + name)
+
+    def __call__(self, *a, **k):
+        raise RuntimeError("%s is a stub: the real package is not installed in this image" % self._path)
+
+    def __repr__(self):
+        return "<stub %s>" % self._path
+
+
+class _StubModule(types.ModuleType):
+    """`from rdkit.Chem.rdMolDescriptors import GetMorganFingerprintAsBitVect` succeeds at import time."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Placeholder(self.__name__ + "." + name)
+
+
 def _stub_missing():
     """rdkit / tensorboardX are imported at module top by loader.py / the scripts but never reached on this path."""
     for name in ("rdkit", "rdkit.Chem", "rdkit.Chem.Descriptors", "rdkit.Chem.AllChem", "rdkit.DataStructs",
@@ -68,7 +96,7 @@ def _stub_missing():
         try:
             importlib.import_module(name)
         except Exception:
-            m = types.ModuleType(name)
+            m = _StubModule(name)
             m.__stub__ = True
             sys.modules[name] = m
             if "." in name:

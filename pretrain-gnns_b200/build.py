@@ -14,8 +14,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libpgnn_b200.so")
+# PGNN_BUILD_DIR / PGNN_LIB_OUT: scratch build elsewhere (compile checks that must not touch the in-tree library)
+OBJ = os.environ.get("PGNN_BUILD_DIR") or os.path.join(HERE, "csrc", "_obj")
+LIB = os.environ.get("PGNN_LIB_OUT") or os.path.join(HERE, "libpgnn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]

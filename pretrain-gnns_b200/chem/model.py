@@ -150,14 +150,19 @@ class GNN(nn.Module):
         self._plan = None          # lazily built bookkeeping of the fused GIN path (ops.ChemGinPlan)
         self.fused = True          # set False to force the layer-by-layer composition (used by the tests)
 
+    _DEFAULT_AGGR = {"gin": "add", "gcn": "add", "gat": "add", "graphsage": "mean"}
+
     def _fused_plan(self):
-        """The whole-encoder kernels cover gnn_type='gin', JK='last', sum aggregation, no live dropout."""
-        if not (self.fused and self._gnn_type == "gin" and self.JK == "last" and (self.drop_ratio == 0 or not self.training)):
+        """The whole-encoder kernels (pgnn_chem_gin_* / pgnn_chem_conv_*) cover every gnn_type with JK='last', the conv's
+        default aggregation (and GAT's 2 heads / slope 0.2) and no live dropout."""
+        if not (self.fused and self.JK == "last" and (self.drop_ratio == 0 or not self.training)):
             return None
-        if any(conv.aggr != "add" for conv in self.gnns) or any(bn.training != self.training for bn in self.batch_norms):
+        if any(conv.aggr != self._DEFAULT_AGGR[self._gnn_type] for conv in self.gnns) or any(bn.training != self.training for bn in self.batch_norms):
+            return None
+        if self._gnn_type == "gat" and any(conv.heads != 2 or conv.negative_slope != 0.2 for conv in self.gnns):
             return None
         if self._plan is None:
-            self._plan = ops.ChemGinPlan(self)
+            self._plan = ops.ChemGinPlan(self) if self._gnn_type == "gin" else ops.ChemConvPlan(self, self._gnn_type)
         return self._plan
 
     def forward(self, *argv):
@@ -169,7 +174,8 @@ class GNN(nn.Module):
             raise ValueError("unmatched number of arguments.")
         plan = self._fused_plan()
         if plan is not None:
-            return ops.chem_gin_encoder(plan, x, edge_index, edge_attr, self.training)
+            enc = ops.chem_gin_encoder if self._gnn_type == "gin" else ops.chem_conv_encoder
+            return enc(plan, x, edge_index, edge_attr, self.training)
         graph = ops.graph_for(edge_index, x.size(0))
         h = ops.chem_embed(x, self.x_embedding1.weight, self.x_embedding2.weight)
         hs = [h]

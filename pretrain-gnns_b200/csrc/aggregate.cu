@@ -76,16 +76,32 @@ k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restric
       }
       axpy4(acc, __fmul_rn(di, di), affine_act(ld4(x + (int64_t)i * ldx + c), in_scale, in_shift, c, in_relu));
     } else {
+      // the self-loop row and up to four neighbour rows are in flight together (the chain rowptr -> nbr -> row is three
+      // dependent L2 round trips per thread: memory-level parallelism, not bandwidth, bounds this kernel); the additions keep
+      // the edge order, self-loop last, so the row sums stay bit-identical to a sequential index_add_
+      const float4 vself = ld4(x + (int64_t)i * ldx + c);
       int k = lo;
-      for (; k + 1 < hi; k += 2) {  // two independent row loads in flight
+      for (; k + 3 < hi; k += 4) {
+        const int s0 = nbr[k], s1 = nbr[k + 1], s2 = nbr[k + 2], s3 = nbr[k + 3];
+        const float4 v0 = ld4(x + (int64_t)s0 * ldx + c);
+        const float4 v1 = ld4(x + (int64_t)s1 * ldx + c);
+        const float4 v2 = ld4(x + (int64_t)s2 * ldx + c);
+        const float4 v3 = ld4(x + (int64_t)s3 * ldx + c);
+        add4(acc, affine_act(v0, in_scale, in_shift, c, in_relu));
+        add4(acc, affine_act(v1, in_scale, in_shift, c, in_relu));
+        add4(acc, affine_act(v2, in_scale, in_shift, c, in_relu));
+        add4(acc, affine_act(v3, in_scale, in_shift, c, in_relu));
+      }
+      if (k + 1 < hi) {
         const int s0 = nbr[k], s1 = nbr[k + 1];
         const float4 v0 = ld4(x + (int64_t)s0 * ldx + c);
         const float4 v1 = ld4(x + (int64_t)s1 * ldx + c);
         add4(acc, affine_act(v0, in_scale, in_shift, c, in_relu));
         add4(acc, affine_act(v1, in_scale, in_shift, c, in_relu));
+        k += 2;
       }
       if (k < hi) add4(acc, affine_act(ld4(x + (int64_t)nbr[k] * ldx + c), in_scale, in_shift, c, in_relu));
-      add4(acc, affine_act(ld4(x + (int64_t)i * ldx + c), in_scale, in_shift, c, in_relu));  // self-loop last
+      add4(acc, affine_act(vself, in_scale, in_shift, c, in_relu));  // self-loop last
       if (mode == PGNN_AGG_MEAN) {
         const float cnt = (float)(hi - lo + 1);
         acc.x = __fdiv_rn(acc.x, cnt);
@@ -99,6 +115,7 @@ k_aggregate_fwd(const float* __restrict__ x, int64_t ldx, const float* __restric
       const float* s = S + (int64_t)i * Q;
       for (int q = 0; q < Q; ++q) {
         const float w = s[q];
+        if (w == 0.f) continue;  // most of a node's 9-10 summary bins are empty; fmaf(0, t, e) == e, so skipping is exact
         const float4 t = ld4(q < q_split ? T + (int64_t)q * C + c : T2 + (int64_t)(q - q_split) * C + c);
         e.x = fmaf(w, t.x, e.x);
         e.y = fmaf(w, t.y, e.y);
@@ -128,15 +145,28 @@ k_aggregate_bwd(const float* __restrict__ g, int64_t ldg, int64_t n, int C4, con
     const int lo = rowptr_s[j], hi = rowptr_s[j + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (mode == PGNN_AGG_SUM) {
+      const float4 vself = ld4(g + (int64_t)j * ldg + c);
       int k = lo;
-      for (; k + 1 < hi; k += 2) {
+      for (; k + 3 < hi; k += 4) {
+        const int t0 = nbr_s[k], t1 = nbr_s[k + 1], t2 = nbr_s[k + 2], t3 = nbr_s[k + 3];
+        const float4 v0 = ld4(g + (int64_t)t0 * ldg + c);
+        const float4 v1 = ld4(g + (int64_t)t1 * ldg + c);
+        const float4 v2 = ld4(g + (int64_t)t2 * ldg + c);
+        const float4 v3 = ld4(g + (int64_t)t3 * ldg + c);
+        add4(acc, v0);
+        add4(acc, v1);
+        add4(acc, v2);
+        add4(acc, v3);
+      }
+      if (k + 1 < hi) {
         const float4 v0 = ld4(g + (int64_t)nbr_s[k] * ldg + c);
         const float4 v1 = ld4(g + (int64_t)nbr_s[k + 1] * ldg + c);
         add4(acc, v0);
         add4(acc, v1);
+        k += 2;
       }
       if (k < hi) add4(acc, ld4(g + (int64_t)nbr_s[k] * ldg + c));
-      add4(acc, ld4(g + (int64_t)j * ldg + c));
+      add4(acc, vself);
     } else {
       for (int k = lo; k < hi; ++k) {
         const int t = nbr_s[k];
@@ -193,20 +223,49 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
 
 __global__ void __launch_bounds__(256)
 k_chem_embed_fwd(const int64_t* __restrict__ x, const float* __restrict__ t1, const float* __restrict__ t2, int64_t n,
-                 int C4, float* __restrict__ out, int64_t ldo) {
+                 int C4, int rows1, int rows2, float* __restrict__ out, int64_t ldo, unsigned int* __restrict__ err) {
   pdl_prologue();
   const int64_t total = n * C4;
   const int C = C4 * 4;
+  bool bad = false;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = idx / C4;
     const int c = (int)(idx - i * C4) * 4;
-    const float4 a = ld4(t1 + x[2 * i] * C + c), b = ld4(t2 + x[2 * i + 1] * C + c);
+    int64_t a0 = x[2 * i], a1 = x[2 * i + 1];
+    if (a0 < 0 || a0 >= rows1 || a1 < 0 || a1 >= rows2) {  // nn.Embedding would raise (chem/model.py:231-232): flag, use row 0
+      bad = true;
+      a0 = (a0 < 0 || a0 >= rows1) ? 0 : a0;
+      a1 = (a1 < 0 || a1 >= rows2) ? 0 : a1;
+    }
+    const float4 a = ld4(t1 + a0 * C + c), b = ld4(t2 + a1 * C + c);
     st4(out + i * ldo + c, make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w)));
+  }
+  if (bad && err) atomicOr(err, (unsigned)PGNN_DEVERR_ATOM_CODE);
+}
+
+// One-hot rows of the two atom codes side by side: oh[i][x0] = 1, oh[i][rows1 + x1] = 1, width padded to a multiple of 4.
+// With it the embedding gradient [rows1 + rows2, C] = oh^T . g is a weight-gradient GEMM on the tensor cores (exact products,
+// split-K folded in a fixed order: bit-reproducible) instead of N*C/4 vector atomics onto 123 rows (encoder.cu).
+__global__ void __launch_bounds__(256)
+k_chem_onehot(const int64_t* __restrict__ x, int64_t n, int rows1, int rows2, float* __restrict__ oh, int ld4s) {
+  pdl_prologue();
+  const int64_t total = n * ld4s;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / ld4s;
+    const int c = (int)(idx - i * ld4s) * 4;
+    const int64_t a0 = x[2 * i], a1 = x[2 * i + 1];
+    const int h0 = (a0 >= 0 && a0 < rows1) ? (int)a0 : -1, h1 = (a1 >= 0 && a1 < rows2) ? rows1 + (int)a1 : -1;
+    float4 v;
+    v.x = (c == h0 || c == h1) ? 1.f : 0.f;
+    v.y = (c + 1 == h0 || c + 1 == h1) ? 1.f : 0.f;
+    v.z = (c + 2 == h0 || c + 2 == h1) ? 1.f : 0.f;
+    v.w = (c + 3 == h0 || c + 3 == h1) ? 1.f : 0.f;
+    st4(oh + idx * 4, v);
   }
 }
 
 __global__ void __launch_bounds__(256)
-k_chem_embed_bwd(const int64_t* __restrict__ x, const float* __restrict__ g, int64_t ldg, int64_t n, int C4,
+k_chem_embed_bwd(const int64_t* __restrict__ x, const float* __restrict__ g, int64_t ldg, int64_t n, int C4, int rows1, int rows2,
                  float* __restrict__ g1, float* __restrict__ g2) {
   pdl_prologue();
   const int64_t total = n * C4;
@@ -215,8 +274,9 @@ k_chem_embed_bwd(const int64_t* __restrict__ x, const float* __restrict__ g, int
     const int64_t i = idx / C4;
     const int c = (int)(idx - i * C4) * 4;
     const float4 v = ld4(g + i * ldg + c);
-    atomicAdd(reinterpret_cast<float4*>(g1 + x[2 * i] * C + c), v);
-    atomicAdd(reinterpret_cast<float4*>(g2 + x[2 * i + 1] * C + c), v);
+    const int64_t a0 = x[2 * i], a1 = x[2 * i + 1];  // out-of-range codes were flagged by the forward; they get no gradient
+    if (a0 >= 0 && a0 < rows1) atomicAdd(reinterpret_cast<float4*>(g1 + a0 * C + c), v);
+    if (a1 >= 0 && a1 < rows2) atomicAdd(reinterpret_cast<float4*>(g2 + a1 * C + c), v);
   }
 }
 
@@ -291,6 +351,15 @@ int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_sca
   return PGNN_OK;
 }
 
+int pgnn_internal_chem_onehot(const int64_t* x, int64_t n, int rows1, int rows2, float* onehot, int64_t ld, cudaStream_t st) {
+  if (n == 0) return PGNN_OK;
+  if (ld % 4 || ld < rows1 + rows2 || !aligned16(onehot)) return PGNN_EUNSUPPORTED;
+  const int ld4s = (int)(ld / 4);
+  PGNN_CUDA(pgnn_launch(k_chem_onehot, dim3(grid_items(n * ld4s, 256)), dim3(256), 0, st, x, n, rows1, rows2, onehot, ld4s));
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
 extern "C" {
 
 int pgnn_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
@@ -331,14 +400,15 @@ int pgnn_edge_table_bwd(const float* S, int64_t Q, const float* g, int64_t ldg, 
   return pgnn_internal_edge_table_bwd(S, (int)Q, g, ldg, g_off, num_nodes, (int)C, gT, C, st);
 }
 
-int pgnn_chem_embed_fwd(const int64_t* x, const float* tab1, const float* tab2, int64_t num_nodes, int64_t C, float* out,
-                        int64_t ldo, void* stream) {
+int pgnn_chem_embed_fwd(const int64_t* x, const float* tab1, int64_t rows1, const float* tab2, int64_t rows2, int64_t num_nodes,
+                        int64_t C, float* out, int64_t ldo, void* stream) {
   PGNN_CHECK_ARG(num_nodes >= 0 && C > 0);
   if (num_nodes == 0) return PGNN_OK;
-  PGNN_CHECK_ARG(x && tab1 && tab2 && out);
+  PGNN_CHECK_ARG(x && tab1 && tab2 && out && rows1 > 0 && rows2 > 0);
   if (C % 4 || ldo % 4 || !aligned16(tab1) || !aligned16(tab2) || !aligned16(out)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  PGNN_CUDA(pgnn_launch(k_chem_embed_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, as_stream(stream), x, tab1, tab2, num_nodes, C4, out, ldo));
+  PGNN_CUDA(pgnn_launch(k_chem_embed_fwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, as_stream(stream), x, tab1, tab2, num_nodes, C4, (int)rows1, (int)rows2, out, ldo,
+                        pgnn_error_flag_ptr()));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -353,7 +423,7 @@ int pgnn_chem_embed_bwd(const int64_t* x, const float* g, int64_t ldg, int64_t n
   PGNN_CHECK_ARG(x && g);
   if (C % 4 || ldg % 4 || !aligned16(g) || !aligned16(gtab1) || !aligned16(gtab2)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  PGNN_CUDA(pgnn_launch(k_chem_embed_bwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, st, x, g, ldg, num_nodes, C4, gtab1, gtab2));
+  PGNN_CUDA(pgnn_launch(k_chem_embed_bwd, dim3(grid_items(num_nodes * C4, 256)), dim3(256), 0, st, x, g, ldg, num_nodes, C4, (int)rows1, (int)rows2, gtab1, gtab2));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -43,7 +43,34 @@ void pgnn_profile_mark(const void* kernel, cudaStream_t st, bool after) {
   }
 }
 
+unsigned int* pgnn_error_flag_ptr() {
+  static std::mutex mu;
+  static unsigned int* ptr[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> g(mu);
+  if (!ptr[dev]) {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(unsigned int)) != cudaSuccess || cudaMemset(p, 0, sizeof(unsigned int)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    ptr[dev] = p;
+  }
+  return ptr[dev];
+}
+
 extern "C" {
+
+int pgnn_device_error_flags(int clear) {
+  unsigned int* p = pgnn_error_flag_ptr();
+  if (!p) return PGNN_ECUDA;
+  unsigned int v = 0;
+  PGNN_CUDA(cudaDeviceSynchronize());
+  PGNN_CUDA(cudaMemcpy(&v, p, sizeof v, cudaMemcpyDeviceToHost));
+  if (clear && v) PGNN_CUDA(cudaMemset(p, 0, sizeof v));
+  return (int)(v & 0x7fffffffu);
+}
 
 int pgnn_version(void) { return 100; }
 

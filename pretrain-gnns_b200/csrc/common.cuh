@@ -13,6 +13,10 @@ extern std::atomic<long long> g_pgnn_kernel_launches;  // every kernel this libr
 extern std::atomic<int> g_pgnn_profile_on;
 void pgnn_profile_mark(const void* kernel, cudaStream_t st, bool after);
 
+// Device error word of the current device (lazily allocated, zeroed): kernels that consume indices OR a PGNN_DEVERR_* bit into
+// it instead of reading or writing out of range; pgnn_device_error_flags() reads it back.  May return null (then unchecked).
+unsigned int* pgnn_error_flag_ptr();
+
 #define PGNN_CHECK_ARG(cond)            \
   do {                                  \
     if (!(cond)) return PGNN_EINVAL;    \
@@ -97,6 +101,11 @@ struct TcEpilogue {
   int atomic;             // split-K: accumulate with atomics into a zeroed output
   PgnnGemmHooks hooks;    // fused column reductions over the final output tile (not with split-K)
   int64_t split_stride = 0;  // split-K without atomics: split z stores its tile at C + z * split_stride (folded afterwards)
+  // In-kernel fold of those partial tiles (TMA kernel only; requires every CTA of the grid to be co-resident): after storing
+  // its partial tile a CTA bumps fold_counter[tile], waits until all `gridDim.z` splits of the tile have arrived, and sums a
+  // 1/gridDim.z row slice of the tile over the splits IN SPLIT ORDER (bit-reproducible) into fold_out (leading dimension ldc).
+  unsigned int* fold_counter = nullptr;  // [tiles], zero before the launch
+  float* fold_out = nullptr;
 };
 
 // B200: 148 SMs.  Grids for grid-stride kernels are sized as a multiple of this.

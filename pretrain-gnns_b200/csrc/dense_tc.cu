@@ -325,16 +325,22 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, i
 //   * if some width covers the problem in ONE wave (<= 148 CTAs incl. splits), take the narrowest such width:
 //     least work per CTA, most SMs busy;
 //   * otherwise (many waves) operand re-reads dominate: take the widest width with <= 15% padding waste.
-inline int pick_bn(int M, int N, int splits) {
+// `kk`: both operands reduction-contiguous on the TMA kernel, whose B box is [BN rows x 32 k] for any BN % 16 == 0; there the
+// widths 112 and 208 exist as well: N = 300 tiles as 3 x 112 (11% padding instead of 28% with 3 x 128) and N = 600 as 3 x 208
+// (4% instead of 12% with 3 x 224) — the tensor time of a block is proportional to BN.  The MN-major boxes (32 rows each) and
+// the cp.async kernel need BN % 32 == 0.
+inline int pick_bn(int M, int N, int splits, bool kk = false) {
   if (const char* e = getenv("PGNN_BN")) {  // development override
     const int v = atoi(e);
-    if (v == 64 || v == 128 || v == 160 || v == 224) return v;
+    if (v == 64 || v == 128 || v == 160 || v == 224 || (kk && (v == 112 || v == 208))) return v;
   }
-  const int cand[4] = {64, 128, 160, 224};
+  const int cand_kk[6] = {64, 112, 128, 160, 208, 224}, cand_32[4] = {64, 128, 160, 224};
+  const int* cand = kk ? cand_kk : cand_32;
+  const int nc = kk ? 6 : 4;
   const int64_t mt = ceil_div(M, BM) * (splits > 0 ? splits : 1);
-  for (int bn : cand)
-    if (mt * ceil_div(N, bn) <= kNumSMs) return bn;
-  for (int i = 3; i >= 0; --i) {
+  for (int i = 0; i < nc; ++i)
+    if (mt * ceil_div(N, cand[i]) <= kNumSMs) return cand[i];
+  for (int i = nc - 1; i >= 0; --i) {
     const int bn = cand[i];
     const int padded = (int)ceil_div(N, bn) * bn;
     if (padded <= N + N * 15 / 100 || bn == 64) return bn;
@@ -391,7 +397,7 @@ int pgnn_tc_linear_fwd(const float* x, int64_t ldx, const float* w, const float*
   if (K % 4 || ldx % 4 || !aligned16(x) || !aligned16(w) || !aligned16(y) || M < 1) return PGNN_EUNSUPPORTED;
   TcEpilogue ep{bias, relu, nullptr, 0, 0, hooks ? *hooks : PgnnGemmHooks{}};
   if (tma_enabled()) {  // both operands reduction-contiguous: TMA-staged kernel (dense_tma.cu)
-    const int rc = pgnn_tma_gemm_kk(pick_bn((int)M, (int)N, 1), x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, ep, st);
+    const int rc = pgnn_tma_gemm_kk(pick_bn((int)M, (int)N, 1, true), x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, ep, st);
     if (rc != PGNN_EUNSUPPORTED) return rc;
   }
   return dispatch<true, true>(pick_bn((int)M, (int)N, 1), x, ldx, w, K, y, ldy, (int)M, (int)N, (int)K, 1, (int)K, ep, st);
@@ -417,7 +423,7 @@ int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int6
                             int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks) {
   if (!tma_enabled() || N % 4 || ldgy % 4 || !aligned16(gy) || !aligned16(wT) || !aligned16(gx) || M < 1) return PGNN_EUNSUPPORTED;
   TcEpilogue ep{nullptr, 0, relu_src, ldr, 0, hooks ? *hooks : PgnnGemmHooks{}};
-  return pgnn_tma_gemm_kk(pick_bn((int)M, (int)K, 1), gy, ldgy, wT, N, gx, ldgx, (int)M, (int)K, (int)N, ep, st);
+  return pgnn_tma_gemm_kk(pick_bn((int)M, (int)K, 1, true), gy, ldgy, wT, N, gx, ldgx, (int)M, (int)K, (int)N, ep, st);
 }
 
 // out[c][r] = in[r][c] for a batch of row-major matrices (weights: a few hundred KB each)
@@ -482,7 +488,35 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
 }
 }  // namespace
 
-int64_t pgnn_tc_wgrad_workspace_floats(int64_t N, int64_t K) { return (int64_t)kNumSMs * N * K / 8 + N * K; }  // generous bound: splits <= 148 / tiles
+namespace {
+// tile width, split count and rows per split of the weight-gradient GEMM gw[N,K] = gy[M,N]^T . x[M,K]
+struct WgradPlan { int bn, tiles, splits, per; };
+WgradPlan wgrad_plan(int64_t M, int64_t N, int64_t K) {
+  WgradPlan p;
+  p.bn = 224;  // the reduction is long and both operands are re-read per tile: widest tile with <= 15% padding
+  for (int c : {224, 160, 128, 64}) {
+    p.bn = c;
+    if ((int)ceil_div(K, c) * c <= K + K * 15 / 100) break;
+  }
+  p.tiles = (int)(ceil_div(N, BM) * ceil_div(K, p.bn));
+  int splits = kNumSMs / p.tiles;  // floor: 150 CTAs on 148 SMs would run as two waves
+  // the tensor core accumulates with truncation: keep each TMEM chain <= 1024 rows, fold the rest in fp32
+  if (splits < (int)ceil_div(M, 1024)) splits = (int)ceil_div(M, 1024);
+  const int max_splits = (int)ceil_div(M, 2 * BK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.per = (int)align_up(ceil_div(M, splits), 32);  // multiple of the TMA kernel's 32-deep block (and of BK)
+  p.splits = (int)ceil_div(M, p.per);
+  return p;
+}
+}  // namespace
+
+// floats of split-K workspace pgnn_tc_linear_bwd_w_ws needs for this problem: one partial tile set per split + the arrival counters
+int64_t pgnn_tc_wgrad_workspace_floats(int64_t M, int64_t N, int64_t K) {
+  if (M < 1) M = 1;
+  const WgradPlan p = wgrad_plan(M, N, K);
+  return (int64_t)p.splits * N * K + align_up(p.tiles, 4) + 64;
+}
 
 // gw[N,K] = gy[M,N]^T . x[M,K]; gb[N] = column sums of gy.  `partials` (optional, >= splits*N*K floats): split-K partial
 // tiles are stored there and folded by one reduction kernel; without it the epilogue uses vector atomics.
@@ -494,33 +528,50 @@ int pgnn_tc_linear_bwd_w(const float* gy, int64_t ldgy, const float* x, int64_t 
   return pgnn_tc_linear_bwd_w_ws(gy, ldgy, x, ldx, M, N, K, gw, gb, nullptr, 0, st);
 }
 
+static int device_sm_count() {
+  static int n = -1;
+  if (n < 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 1;
+  }
+  return n;
+}
+static bool fold_in_kernel_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_SPLITK_FOLD");  // "kernel" (default) | "separate": the fold as its own launch (k_splitk_reduce)
+    v = (e && e[0] == 's') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st) {
   if (K % 4 || ldgy % 4 || ldx % 4 || !aligned16(gy) || !aligned16(x) || !aligned16(gw) || M < 1) return PGNN_EUNSUPPORTED;
   if ((N % 4) && !tma_enabled()) return PGNN_EUNSUPPORTED;  // ragged N (e.g. 119 classes) only through the TMA boxes
   // output [N, K] (rows N = "M" of the MMA), reduction over the M node rows, split so the grid fills the chip
-  int bn = 224;  // the reduction is long and both operands are re-read per tile: widest tile with <= 15% padding
-  for (int c : {224, 160, 128, 64}) {
-    bn = c;
-    if ((int)ceil_div(K, c) * c <= K + K * 15 / 100) break;
-  }
-  const int tiles = (int)(ceil_div(N, BM) * ceil_div(K, bn));
-  int splits = kNumSMs / tiles;  // floor: 150 CTAs on 148 SMs would run as two waves
-  // the tensor core accumulates with truncation: keep each TMEM chain <= 1024 rows, fold the rest in fp32 atomics
-  if (splits < (int)ceil_div(M, 1024)) splits = (int)ceil_div(M, 1024);
-  const int max_splits = (int)ceil_div(M, 2 * BK);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  int per = (int)align_up(ceil_div(M, splits), 32);  // multiple of the TMA kernel's 32-deep block (and of BK)
-  splits = (int)ceil_div(M, per);
+  const WgradPlan plan = wgrad_plan(M, N, K);
+  const int bn = plan.bn, tiles = plan.tiles, splits = plan.splits, per = plan.per;
   int rc = PGNN_EUNSUPPORTED;
   const bool two_phase = splits > 1 && partials && partial_floats >= (int64_t)splits * N * K && tma_enabled() && ((N * K) % 4 == 0);
   if (two_phase) {
     // split s writes its tile into partials[s] (the kernel offsets C by blockIdx.z * N * ldc through ep.split_stride)
     TcEpilogue ep{nullptr, 0, nullptr, 0, 0, PgnnGemmHooks{}};
     ep.split_stride = N * K;
+    // The fold runs inside the GEMM when its whole grid is resident at once (one 220 KB CTA per SM): the counters sit behind
+    // the partial tiles in the workspace.
+    const int64_t ctr_floats = align_up(tiles, 4);
+    const bool in_kernel = fold_in_kernel_enabled() && (int64_t)tiles * splits <= device_sm_count() && (K % 4) == 0 &&
+                           partial_floats >= (int64_t)splits * N * K + ctr_floats;
+    if (in_kernel) {
+      unsigned int* ctr = reinterpret_cast<unsigned int*>(partials + (int64_t)splits * N * K);
+      PGNN_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned int) * tiles, st));
+      ep.fold_counter = ctr;
+      ep.fold_out = gw;
+    }
     rc = pgnn_tma_gemm(true, true, bn, gy, ldgy, x, ldx, partials, K, (int)N, (int)K, (int)M, splits, per, ep, st);
-    if (rc == PGNN_OK) {
+    if (rc == PGNN_OK && !in_kernel) {
       const int64_t n4 = N * K / 4;
       int blocks = (int)ceil_div(n4, 256);
       if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;

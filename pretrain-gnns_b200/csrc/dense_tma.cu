@@ -129,11 +129,50 @@ __device__ __forceinline__ uint64_t tma_desc(uint32_t base, int j) {
   return umma_desc_sw128(base + j * 32);                         // 8 fp32 = 32 B inside the 128 B swizzle row
 }
 
+// Split-K fold inside the GEMM (TcEpilogue::fold_counter).  Called by the 256 epilogue threads after their partial tile is
+// stored.  The wait is a spin on a global counter: legal only because the host launches this mode with at most one CTA per SM
+// of the device (every CTA of the grid is resident, none can be waiting for a slot behind a spinning one); time-bounded.
+template <int BN>
+__device__ __forceinline__ void splitk_fold_in_kernel(const float* __restrict__ part, int64_t ldc, int m0, int n0, int M, int N,
+                                                      const TcEpilogue& ep) {
+  const unsigned splits = gridDim.z;
+  unsigned int* ctr = ep.fold_counter + (blockIdx.y * gridDim.x + blockIdx.x);
+  asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");   // every thread's stores of the partial tile are issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const uint64_t t0 = globaltimer_ns();
+    unsigned seen = 0;
+    for (uint32_t it = 0;; ++it) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      if (seen >= splits) break;
+      if ((it & 255u) == 255u && globaltimer_ns() - t0 > 2000000000ull) asm volatile("trap;");
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
+  const int rows_here = min(BM, M - m0);
+  const int cols_here = min(BN, N - n0);         // N % 4 == 0 in this mode (checked by the host)
+  const int per = (rows_here + (int)splits - 1) / (int)splits;
+  const int r0 = (int)blockIdx.z * per, r1 = min(rows_here, r0 + per);
+  const int C4 = cols_here >> 2;
+  for (int idx = threadIdx.x; idx < (r1 - r0) * C4; idx += NPRODUCER) {
+    const int r = r0 + idx / C4, c = (idx - (idx / C4) * C4) * 4;
+    const int64_t off = (int64_t)(m0 + r) * ldc + n0 + c;
+    float4 a = __ldcg(reinterpret_cast<const float4*>(part + off));
+    for (unsigned sp = 1; sp < splits; ++sp) {   // fixed order 0, 1, 2, ...: the result does not depend on arrival order
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)sp * ep.split_stride + off));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(ep.fold_out + off) = a;
+  }
+}
+
 template <bool A_MN, bool B_MN, int BN, bool PAIR>
 __global__ void __launch_bounds__(T_NTHREADS, 1)
 k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
                   int64_t ldc, int M, int N, int K, int k_per_split, TcEpilogue ep) {
   static_assert(!PAIR || (!A_MN && !B_MN && BN % 32 == 0), "the pair variant takes K-major operands; UMMA N % 16 == 0 at M = 256");
+  static_assert(BN % 16 == 0 && BN <= 256 && (!B_MN || BN % 32 == 0), "UMMA N % 16 == 0 at M = 128; MN-major B boxes hold 32 rows");
   using Cfg = TmaCfg<BN, PAIR>;
   constexpr int NRAW = Cfg::NRAW, T_NLO = Cfg::NLO;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -305,6 +344,7 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 0) TC_TRACE(6);
 #ifndef PGNN_UB_NO_EPILOGUE
     tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
+    if (ep.fold_counter) splitk_fold_in_kernel<BN>(C, ldc, m0, n0, M, N, ep);
 #endif
     if (warp == 0) TC_TRACE(7);
   }
@@ -432,6 +472,10 @@ int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* 
 template <bool A_MN, bool B_MN>
 int dispatch_tma(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
                  int splits, int k_per_split, const TcEpilogue& ep, cudaStream_t st) {
+  if constexpr (!A_MN && !B_MN) {  // K-major boxes take any BN % 16 == 0
+    if (bn == 112) return launch_tma<A_MN, B_MN, 112>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+    if (bn == 208) return launch_tma<A_MN, B_MN, 208>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
+  }
   switch (bn) {
     case 64: return launch_tma<A_MN, B_MN, 64>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
     case 128: return launch_tma<A_MN, B_MN, 128>(A, lda, B, ldb, C, ldc, M, N, K, splits, k_per_split, ep, st);
@@ -458,6 +502,18 @@ int pgnn_tma_gemm(bool a_mn, bool b_mn, int bn, const float* A, int64_t lda, con
 extern "C" __attribute__((visibility("default"))) int pgnn_debug_tma_trace(unsigned long long* host16) {
   return cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
 }
+
+#ifdef PGNN_TRACE_ALL
+// reset != 0: prime the envelope (min = ~0, max = 0) before the launch of interest; else read [min 16 | max 16]
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_tma_trace_env(unsigned long long* host32, int reset) {
+  if (reset) {
+    unsigned long long init[32];
+    for (int i = 0; i < 16; ++i) { init[i] = ~0ull; init[16 + i] = 0ull; }
+    return cudaMemcpyToSymbol(g_tc_trace_env, init, sizeof init) == cudaSuccess ? 0 : -2;
+  }
+  return cudaMemcpyFromSymbol(host32, g_tc_trace_env, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int pgnn_tma_gemm_kk(int bn, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
                      const TcEpilogue& ep, cudaStream_t st) {

@@ -17,6 +17,8 @@ int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_sca
                                 const float* S, int64_t Q, const float* T, const float* T2, int q_split, int64_t edge_off, float* out,
                                 int64_t ldo, cudaStream_t st, const PgnnBnFold* fold);
 
+int pgnn_internal_chem_onehot(const int64_t* x, int64_t n, int rows1, int rows2, float* onehot, int64_t ld, cudaStream_t st);
+
 int pgnn_tc_linear_fwd(const float*, int64_t, const float*, const float*, int64_t, int64_t, int64_t, int, float*, int64_t,
                        cudaStream_t, const PgnnGemmHooks*);
 int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, int64_t, const float*, int64_t, float*, int64_t,
@@ -24,7 +26,7 @@ int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, 
 int pgnn_tc_linear_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
 int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st);
-int64_t pgnn_tc_wgrad_workspace_floats(int64_t N, int64_t K);
+int64_t pgnn_tc_wgrad_workspace_floats(int64_t M, int64_t N, int64_t K);
 int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int64_t M, int64_t N, int64_t K, const float* relu_src,
                             int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks);
 int pgnn_internal_transpose_batch(int count, const float* const* in, float* const* out, const int* rows, const int* cols,
@@ -41,6 +43,9 @@ namespace {
 enum { P_XEMB1 = 0, P_XEMB2 = 1, P_LAYER0 = 2 };
 enum { L_W1 = 0, L_B1, L_W2, L_B2, L_ET1, L_ET2, L_GAMMA, L_BETA, L_COUNT };
 
+constexpr int kAtomRows = 120, kChiralRows = 3;   // chem/model.py:9-10
+constexpr int kOneHotLd = 124;                    // kAtomRows + kChiralRows padded to a multiple of 4
+
 struct Carve {
   char* base;
   int64_t off = 0;
@@ -56,6 +61,8 @@ struct Carve {
 struct Ws {
   int32_t *rowptr_t, *rowptr_s, *nbr_t, *eid_t, *nbr_s, *eid_s;
   float *S, *h0, *scale, *shift, *mean, *invstd;  // scale/shift/mean/invstd: [L, D]
+  float* onehot;                                   // [N, kOneHotLd]: atom-code one-hot rows (embedding gradient as a GEMM)
+  double* bn_acc;                                  // [L][2][D] fp64 BatchNorm sums of the forward
   float *aggr, *z1, *z2;                           // [L, N, D], [L, N, 2D], [L, N, D]
   float *gh, *gz2, *gz1, *gaggr;                   // backward temporaries
   float* wT;                                       // [L][2][2D*D]: mlp.0.weight^T, mlp.2.weight^T (dgrad B operands)
@@ -77,6 +84,8 @@ Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.eid_s = c.take<int32_t>(e1);
   w.S = c.take<float>(N * 9);
   w.h0 = c.take<float>(N * D);
+  w.onehot = c.take<float>(N * kOneHotLd);
+  w.bn_acc = c.take<double>(L * 2 * D);
   w.scale = c.take<float>(L * D);
   w.shift = c.take<float>(L * D);
   w.mean = c.take<float>(L * D);
@@ -89,7 +98,11 @@ Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.gz1 = c.take<float>(N * 2 * D);
   w.gaggr = c.take<float>(N * D);
   w.wT = c.take<float>(L * 4 * D * D);
-  w.wpart_floats = pgnn_tc_wgrad_workspace_floats(2 * D, D);
+  w.wpart_floats = pgnn_tc_wgrad_workspace_floats(N, 2 * D, D);  // both MLP weight gradients have 2D*D elements
+  {
+    const int64_t e = pgnn_tc_wgrad_workspace_floats(N, 123, D);  // the embedding tables' gradient as a GEMM
+    if (e > w.wpart_floats) w.wpart_floats = e;
+  }
   w.wpart = c.take<float>(w.wpart_floats);
   int64_t sb = pgnn_graph_prep_workspace_bytes(N, E);
   const int64_t bb = pgnn_bn_workspace_bytes(N > 0 ? N : 1, D);
@@ -148,12 +161,13 @@ int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mea
   Ws w = carve(workspace, N, E, L, D);
   TRY(pgnn_graph_prep(edge_index, E, N, w.rowptr_t, w.nbr_t, w.eid_t, w.rowptr_s, w.nbr_s, w.eid_s, w.scratch, w.scratch_bytes, stream));
   TRY(pgnn_chem_edge_summary(edge_attr, w.rowptr_t, w.nbr_t, w.eid_t, N, PGNN_AGG_SUM, nullptr, w.S, stream));
-  TRY(pgnn_chem_embed_fwd(x, (const float*)params[P_XEMB1], (const float*)params[P_XEMB2], N, D, w.h0, D, stream));
+  TRY(pgnn_chem_embed_fwd(x, (const float*)params[P_XEMB1], kAtomRows, (const float*)params[P_XEMB2], kChiralRows, N, D, w.h0, D, stream));
+  if (training && precision == 1) TRY(pgnn_internal_chem_onehot(x, N, kAtomRows, kChiralRows, w.onehot, kOneHotLd, as_stream(stream)));
   const float* h = w.h0;            // input rows of the current layer (pre-affine)
   const float *in_scale = nullptr, *in_shift = nullptr;
   PgnnBnFold fold;                  // pending BatchNorm finalisation of the previous layer (folded into this layer's gather)
   bool have_fold = false;
-  double* const bn_acc = reinterpret_cast<double*>(w.gz1);  // [L][2][D] fp64 sums; gz1 is a backward-only buffer
+  double* const bn_acc = w.bn_acc;  // [L][2][D] fp64 sums
   for (int64_t l = 0; l < L; ++l) {
     const void* const* p = params + P_LAYER0 + l * L_COUNT;
     float* aggr = w.aggr + l * N * D;
@@ -301,8 +315,15 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
     gy = w.gh;
     ldgy = D;
   }
-  TRY(pgnn_chem_embed_bwd(x, w.gh, D, N, D, grads + off[P_XEMB1], 120, grads + off[P_XEMB2], 3, stream));
-  return PGNN_OK;
+  // embedding tables: [120 + 3, D] = onehot^T . gh as a split-K weight-gradient GEMM (the two tables are adjacent in the flat
+  // layout); the vector-atomics kernel remains the fallback (FFMA precision, TMA unavailable)
+  int rc_e = PGNN_EUNSUPPORTED;
+  if (precision == 1 && off[P_XEMB2] == off[P_XEMB1] + (int64_t)kAtomRows * D)
+    rc_e = pgnn_tc_linear_bwd_w_ws(w.onehot, kOneHotLd, w.gh, D, N, kAtomRows + kChiralRows, D, grads + off[P_XEMB1], nullptr, w.wpart,
+                                   w.wpart_floats, st);
+  if (rc_e == PGNN_EUNSUPPORTED)
+    rc_e = pgnn_chem_embed_bwd(x, w.gh, D, N, D, grads + off[P_XEMB1], kAtomRows, grads + off[P_XEMB2], kChiralRows, stream);
+  return rc_e;
 }
 
 }  // extern "C"

@@ -45,35 +45,47 @@ k_segment_mean_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __re
 }
 
 __global__ void __launch_bounds__(256)
-k_row_gather_fwd(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
-                 int64_t m, int C4, float* __restrict__ out, int64_t ldo) {
+k_row_gather_fwd(const float* __restrict__ x, int64_t ldx, int64_t rows, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
+                 int64_t m, int C4, float* __restrict__ out, int64_t ldo, unsigned int* __restrict__ err) {
   pdl_prologue();
   const int64_t total = m * C4;
+  bool bad = false;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C4;
     const int c = (int)(idx - r * C4) * 4;
-    float4 v = ld4(x + idx1[r] * ldx + c);
+    const int64_t i1 = idx1[r], i2 = idx2 ? idx2[r] : 0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // an out-of-range index (torch would assert) contributes zeros and is flagged
+    if (i1 >= 0 && i1 < rows) v = ld4(x + i1 * ldx + c); else bad = true;
     if (idx2) {
-      const float4 u = ld4(x + idx2[r] * ldx + c);
-      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      if (i2 >= 0 && i2 < rows) {
+        const float4 u = ld4(x + i2 * ldx + c);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      } else {
+        bad = true;
+      }
     }
     st4(out + r * ldo + c, v);
   }
+  if (bad && err) atomicOr(err, (unsigned)PGNN_DEVERR_GATHER);
 }
 
 // index_put_(accumulate=True): duplicates are legal (two masked bonds may share an atom), so rows are
 // accumulated with vector atomics (red.global.add.v4.f32).
 __global__ void __launch_bounds__(256)
 k_row_gather_bwd(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ idx1, const int64_t* __restrict__ idx2,
-                 int64_t m, int C4, float* __restrict__ gx, int64_t ldgx) {
+                 int64_t m, int C4, float* __restrict__ gx, int64_t ldgx, int64_t rows) {
   pdl_prologue();
   const int64_t total = m * C4;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = idx / C4;
     const int c = (int)(idx - r * C4) * 4;
     const float4 v = ld4(g + r * ldg + c);
-    atomicAdd(reinterpret_cast<float4*>(gx + idx1[r] * ldgx + c), v);
-    if (idx2) atomicAdd(reinterpret_cast<float4*>(gx + idx2[r] * ldgx + c), v);
+    const int64_t i1 = idx1[r];
+    if (i1 >= 0 && i1 < rows) atomicAdd(reinterpret_cast<float4*>(gx + i1 * ldgx + c), v);
+    if (idx2) {
+      const int64_t i2 = idx2[r];
+      if (i2 >= 0 && i2 < rows) atomicAdd(reinterpret_cast<float4*>(gx + i2 * ldgx + c), v);
+    }
   }
 }
 
@@ -120,7 +132,7 @@ k_shifted_rowdot_bwd(const float* __restrict__ g, const float* __restrict__ a, i
 // dlogits = (softmax - onehot) / M, so the backward of the loss needs no kernel of its own.
 __global__ void __launch_bounds__(256)
 k_softmax_ce(const float* __restrict__ logits, int64_t ld, int64_t M, int V, const int64_t* __restrict__ labels,
-             double* __restrict__ loss_mean, float* __restrict__ dlogits, int64_t lddl) {
+             double* __restrict__ loss_mean, float* __restrict__ dlogits, int64_t lddl, unsigned int* __restrict__ err) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += (int64_t)gridDim.x * (blockDim.x >> 5)) {
@@ -134,14 +146,18 @@ k_softmax_ce(const float* __restrict__ logits, int64_t ld, int64_t M, int V, con
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     const double lse = mx + log(se);
-    const int64_t y = labels[r];
+    int64_t y = labels[r];
+    if (y < 0 || y >= V) {  // nll_loss would assert: flag, and let the row contribute log-sum-exp only
+      if (lane == 0 && err) atomicOr(err, (unsigned)PGNN_DEVERR_LABEL);
+      y = -1;
+    }
     const double inv_m = 1.0 / (double)M;
     for (int v = lane; v < V; v += 32) {
       const double p = exp((double)row[v] - lse);
       dlogits[r * lddl + v] = (float)((p - (v == y ? 1.0 : 0.0)) * inv_m);
     }
     for (int v = V + lane; v < lddl; v += 32) dlogits[r * lddl + v] = 0.f;  // padding columns of the 16-byte-aligned row
-    if (lane == 0) atomicAdd(loss_mean, (lse - (double)row[y]) * inv_m);
+    if (lane == 0) atomicAdd(loss_mean, (lse - (y >= 0 ? (double)row[y] : 0.0)) * inv_m);
   }
 }
 
@@ -182,26 +198,27 @@ int pgnn_segment_mean_bwd(const float* g, int64_t ldg, const int64_t* seg, const
   return PGNN_OK;
 }
 
-int pgnn_row_gather_fwd(const float* x, int64_t ldx, const int64_t* idx, const int64_t* idx2, int64_t num_idx, int64_t C,
+int pgnn_row_gather_fwd(const float* x, int64_t ldx, int64_t num_rows, const int64_t* idx, const int64_t* idx2, int64_t num_idx, int64_t C,
                         float* out, int64_t ldo, void* stream) {
-  PGNN_CHECK_ARG(num_idx >= 0 && C > 0);
+  PGNN_CHECK_ARG(num_idx >= 0 && C > 0 && num_rows >= 0);
   if (num_idx == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && idx && out);
   if (C % 4 || ldx % 4 || ldo % 4 || !aligned16(x) || !aligned16(out)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  PGNN_CUDA(pgnn_launch(k_row_gather_fwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), x, ldx, idx, idx2, num_idx, C4, out, ldo));
+  PGNN_CUDA(pgnn_launch(k_row_gather_fwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), x, ldx, num_rows, idx, idx2, num_idx, C4, out, ldo,
+                        pgnn_error_flag_ptr()));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
 
 int pgnn_row_gather_bwd(const float* g, int64_t ldg, const int64_t* idx, const int64_t* idx2, int64_t num_idx, int64_t C,
-                        float* gx, int64_t ldgx, void* stream) {
+                        float* gx, int64_t ldgx, int64_t num_rows, void* stream) {
   PGNN_CHECK_ARG(num_idx >= 0 && C > 0);
   if (num_idx == 0) return PGNN_OK;
   PGNN_CHECK_ARG(g && idx && gx);
   if (C % 4 || ldg % 4 || ldgx % 4 || !aligned16(g) || !aligned16(gx)) return PGNN_EUNSUPPORTED;
   const int C4 = (int)(C / 4);
-  PGNN_CUDA(pgnn_launch(k_row_gather_bwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), g, ldg, idx, idx2, num_idx, C4, gx, ldgx));
+  PGNN_CUDA(pgnn_launch(k_row_gather_bwd, dim3(grid_items(num_idx * C4, 256)), dim3(256), 0, as_stream(stream), g, ldg, idx, idx2, num_idx, C4, gx, ldgx, num_rows));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
@@ -213,7 +230,7 @@ int pgnn_softmax_ce_fwd(const float* logits, int64_t ld, int64_t M, int64_t V, c
   PGNN_CUDA(cudaMemsetAsync(loss_mean, 0, sizeof(double), st));
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(logits && labels && dlogits);
-  PGNN_CUDA(pgnn_launch(k_softmax_ce, dim3(grid_items(M * 32, 256)), dim3(256), 0, st, logits, ld, M, (int)V, labels, loss_mean, dlogits, lddl));
+  PGNN_CUDA(pgnn_launch(k_softmax_ce, dim3(grid_items(M * 32, 256)), dim3(256), 0, st, logits, ld, M, (int)V, labels, loss_mean, dlogits, lddl, pgnn_error_flag_ptr()));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }

@@ -213,6 +213,167 @@ k_bn_bwd_apply_colsum(const float* __restrict__ gy, int64_t ldgy, const float* _
   }
 }
 
+// ---- 16-byte versions of the two BatchNorm-backward sweeps (encoder path: C % 4 == 0, aligned rows) ----------------------
+// Tile = 128 columns (one float4 per lane) x kVecRows rows; warp w walks rows r0 + w, r0 + w + 8, ...: every load is a
+// 512-byte warp access, 4x fewer instructions than the scalar sweeps and 2 x 8 independent loads in flight per thread.
+constexpr int kVecRows = 64;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_stats_v4(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, int relu, double* __restrict__ acc) {
+  pdl_prologue();
+  __shared__ double red[2][8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * kVecRows, r1 = min(M, r0 + kVecRows);
+  double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < C) {
+    const float4 mu = ldg4(mean + c), is = ldg4(invstd + c), ga = ldg4(gamma + c), be = ldg4(beta + c);
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w}, gav[4] = {ga.x, ga.y, ga.z, ga.w},
+                bev[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float4 xv = ldg4(x + (int64_t)r * ldx + c), gv = ldg4(gy + (int64_t)r * ldgy + c);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xhat = (xs[q] - muv[q]) * isv[q];
+        float d = gs[q];
+        if (relu && !(fmaf(xhat, gav[q], bev[q]) > 0.f)) d = 0.f;
+        s0[q] += (double)d;
+        s1[q] += (double)d * (double)xhat;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    red[0][w][lane * 4 + q] = s0[q];
+    red[1][w][lane * 4 + q] = s1[q];
+  }
+  __syncthreads();
+  const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
+  if (blockIdx.x * 128 + col < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[which][k][col];
+    atomicAdd(&acc[(int64_t)which * C + blockIdx.x * 128 + col], t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_bwd_apply_colsum_v4(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x, int64_t ldx, int M, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, int relu, const double* __restrict__ sums, float* __restrict__ ggamma,
+                         float* __restrict__ gbeta, float* __restrict__ gx, int64_t ldgx, float* __restrict__ colsum) {
+  pdl_prologue();
+  __shared__ float red[8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * kVecRows, r1 = min(M, r0 + kVecRows);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    const float4 mu = ldg4(mean + c), is = ldg4(invstd + c), ga = ldg4(gamma + c), be = ldg4(beta + c);
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w}, gav[4] = {ga.x, ga.y, ga.z, ga.w},
+                bev[4] = {be.x, be.y, be.z, be.w};
+    float k1[4], k2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double sd = sums[c + q], sdx = sums[(int64_t)C + c + q];
+      k1[q] = (float)(sd / M);
+      k2[q] = (float)(sdx / M);
+      if (blockIdx.y == 0 && w == 0) {  // finalisation of the statistics pass folded in
+        if (gbeta) gbeta[c + q] = (float)sd;
+        if (ggamma) ggamma[c + q] = (float)sdx;
+      }
+    }
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float4 xv = ldg4(x + (int64_t)r * ldx + c), gv = ldg4(gy + (int64_t)r * ldgy + c);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xhat = (xs[q] - muv[q]) * isv[q];
+        float d = gs[q];
+        if (relu && !(fmaf(xhat, gav[q], bev[q]) > 0.f)) d = 0.f;
+        o[q] = gav[q] * isv[q] * (d - k1[q] - xhat * k2[q]);
+        acc[q] += o[q];
+      }
+      *reinterpret_cast<float4*>(gx + (int64_t)r * ldgx + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) red[w][lane * 4 + q] = acc[q];
+  __syncthreads();
+  if (colsum && threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    atomicAdd(&colsum[blockIdx.x * 128 + threadIdx.x], t);
+  }
+}
+
+// forward statistics and apply in the same 16-byte tiling
+__global__ void __launch_bounds__(256)
+k_bn_stats_v4(const float* __restrict__ x, int64_t ldx, int M, int C, double* __restrict__ acc) {
+  pdl_prologue();
+  __shared__ double red[2][8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * kVecRows, r1 = min(M, r0 + kVecRows);
+  double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < C) {
+#pragma unroll 8
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float4 xv = ldg4(x + (int64_t)r * ldx + c);
+      const double v[4] = {(double)xv.x, (double)xv.y, (double)xv.z, (double)xv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        s0[q] += v[q];
+        s1[q] += v[q] * v[q];
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    red[0][w][lane * 4 + q] = s0[q];
+    red[1][w][lane * 4 + q] = s1[q];
+  }
+  __syncthreads();
+  const int which = threadIdx.x >> 7, col = threadIdx.x & 127;
+  if (blockIdx.x * 128 + col < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[which][k][col];
+    atomicAdd(&acc[(int64_t)which * C + blockIdx.x * 128 + col], t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_apply_v4(const float* __restrict__ x, int64_t ldx, int64_t M, int C4, const float* __restrict__ mean,
+              const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+              float* __restrict__ y, int64_t ldy) {
+  pdl_prologue();
+  const int64_t total = M * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C4;
+    const int c = (int)(idx - r * C4) * 4;
+    const float4 xv = ldg4(x + r * ldx + c), mu = ldg4(mean + c), is = ldg4(invstd + c), ga = ldg4(gamma + c), be = ldg4(beta + c);
+    float4 o;
+    o.x = fmaf((xv.x - mu.x) * is.x, ga.x, be.x);
+    o.y = fmaf((xv.y - mu.y) * is.y, ga.y, be.y);
+    o.z = fmaf((xv.z - mu.z) * is.z, ga.z, be.z);
+    o.w = fmaf((xv.w - mu.w) * is.w, ga.w, be.w);
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(y + r * ldy + c) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_relu_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy) {
   pdl_prologue();
@@ -296,6 +457,17 @@ int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, i
   float* c2 = c1 + C;
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   PGNN_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, st));
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (C % 4 == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && ldgx % 4 == 0 && a16(gy) && a16(x) && a16(gx) && a16(gamma) && a16(beta) &&
+      a16(save_mean) && a16(save_invstd)) {
+    dim3 gv((unsigned)ceil_div(C, 128), (unsigned)ceil_div(M, kVecRows));
+    PGNN_CUDA(pgnn_launch(k_bn_bwd_stats_v4, dim3(gv), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
+    PGNN_LAUNCH_CHECK();
+    PGNN_CUDA(pgnn_launch(k_bn_bwd_apply_colsum_v4, dim3(gv), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd,
+                          relu, (const double*)acc, ggamma, gbeta, gx, ldgx, colsum));
+    PGNN_LAUNCH_CHECK();
+    return PGNN_OK;
+  }
   dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
   PGNN_CUDA(pgnn_launch(k_bn_bwd_stats, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
   PGNN_LAUNCH_CHECK();
@@ -322,15 +494,24 @@ int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const f
   cudaStream_t st = as_stream(stream);
   double* acc = reinterpret_cast<double*>(workspace);
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
-  dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
-  PGNN_CUDA(pgnn_launch(k_bn_stats, dim3(g1), dim3(256), 0, st, x, ldx, (int)M, (int)C, acc));
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool v4 = C % 4 == 0 && ldx % 4 == 0 && a16(x) && a16(gamma) && a16(beta) && a16(save_mean) && a16(save_invstd) &&
+                  (!y || (ldy % 4 == 0 && a16(y)));
+  if (v4) {
+    dim3 gv((unsigned)ceil_div(C, 128), (unsigned)ceil_div(M, kVecRows));
+    PGNN_CUDA(pgnn_launch(k_bn_stats_v4, dim3(gv), dim3(256), 0, st, x, ldx, (int)M, (int)C, acc));
+  } else {
+    dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
+    PGNN_CUDA(pgnn_launch(k_bn_stats, dim3(g1), dim3(256), 0, st, x, ldx, (int)M, (int)C, acc));
+  }
   PGNN_LAUNCH_CHECK();
   PGNN_CUDA(pgnn_launch(k_bn_finalize, dim3((unsigned)ceil_div(C, 128)), dim3(128), 0, st, acc, (int)M, (int)C, gamma, beta, running_mean, running_var,
                                                            num_batches_tracked, momentum, eps, save_mean, save_invstd, scale,
                                                            shift));
   PGNN_LAUNCH_CHECK();
   if (y) {
-    PGNN_CUDA(pgnn_launch(k_bn_apply, dim3(grid_items(M * C, 256)), dim3(256), 0, st, x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy));
+    if (v4) PGNN_CUDA(pgnn_launch(k_bn_apply_v4, dim3(grid_items(M * (C / 4), 256)), dim3(256), 0, st, x, ldx, M, (int)(C / 4), save_mean, save_invstd, gamma, beta, relu, y, ldy));
+    else PGNN_CUDA(pgnn_launch(k_bn_apply, dim3(grid_items(M * C, 256)), dim3(256), 0, st, x, ldx, M, (int)C, save_mean, save_invstd, gamma, beta, relu, y, ldy));
     PGNN_LAUNCH_CHECK();
   }
   return PGNN_OK;
@@ -358,6 +539,19 @@ int pgnn_bn_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int6
   float* c1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(2 * C * 8, 256));
   float* c2 = c1 + C;
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
+  {
+    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (C % 4 == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && ldgx % 4 == 0 && a16(gy) && a16(x) && a16(gx) && a16(gamma) && a16(beta) &&
+        a16(save_mean) && a16(save_invstd)) {
+      dim3 gv((unsigned)ceil_div(C, 128), (unsigned)ceil_div(M, kVecRows));
+      PGNN_CUDA(pgnn_launch(k_bn_bwd_stats_v4, dim3(gv), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
+      PGNN_LAUNCH_CHECK();
+      PGNN_CUDA(pgnn_launch(k_bn_bwd_apply_colsum_v4, dim3(gv), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd,
+                            relu, (const double*)acc, ggamma, gbeta, gx, ldgx, (float*)nullptr));
+      PGNN_LAUNCH_CHECK();
+      return PGNN_OK;
+    }
+  }
   dim3 g1((unsigned)ceil_div(C, 32), (unsigned)ceil_div(M, kStatRows));
   PGNN_CUDA(pgnn_launch(k_bn_bwd_stats, dim3(g1), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
   PGNN_LAUNCH_CHECK();

@@ -102,10 +102,24 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
 
 // development trace: globaltimer stamps of CTA (0,0,0) at the phase boundaries (pgnn_debug_tc_trace reads it)
 __device__ unsigned long long g_tc_trace[16];
+#ifdef PGNN_TRACE_ALL
+// development builds only (tools/ubench_gemm.py): the envelope of every CTA's stamps, [0,16) earliest, [16,32) latest
+__device__ unsigned long long g_tc_trace_env[32];
+#define TC_TRACE(slot)                                                                        \
+  do {                                                                                        \
+    if (lane == 0) {                                                                          \
+      const unsigned long long t__ = globaltimer_ns();                                        \
+      if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_trace[slot] = t__;      \
+      atomicMin(&g_tc_trace_env[slot], t__);                                                  \
+      atomicMax(&g_tc_trace_env[16 + slot], t__);                                             \
+    }                                                                                         \
+  } while (0)
+#else
 #define TC_TRACE(slot)                                                                        \
   do {                                                                                        \
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0) g_tc_trace[slot] = globaltimer_ns(); \
   } while (0)
+#endif
 
 
 // Two fp32 accumulators per tile: hi*hi in columns [0,BN), the two cross terms in [BN,2BN).  The tensor
@@ -131,10 +145,14 @@ __device__ __forceinline__ void tc_epilogue(uint8_t* smem, const float* s_bias, 
   constexpr int SLD = BN + 4;  // staging row stride in floats: 16 B aligned, quarter-warps hit distinct banks
   float* stage = reinterpret_cast<float*>(smem);
   {
+    // columns [0, CSPLIT) go to warps 0-3, [CSPLIT, BN) to warps 4-7; both extents are multiples of the 16-column TMEM load
+    constexpr int CSPLIT = (BN + 31) / 32 * 16;
+    static_assert(BN % 16 == 0, "the epilogue reads TMEM 16 columns at a time");
     const int row = (warp & 3) * 32 + lane;
-    const int cbeg = (warp >> 2) * (BN / 2);
+    const int cbeg = (warp >> 2) * CSPLIT;
+    const int cnum = (warp >> 2) ? BN - CSPLIT : CSPLIT;
 #pragma unroll 1
-    for (int c = 0; c < BN / 2; c += 16) {
+    for (int c = 0; c < cnum; c += 16) {
       float v[16];
       if (nkb > 0) {
         float x[16];

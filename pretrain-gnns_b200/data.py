@@ -59,6 +59,11 @@ class MoleculeStore:
         return (int((self.node_ptr_host[ids + 1] - self.node_ptr_host[ids]).sum()),
                 int((self.edge_ptr_host[ids + 1] - self.edge_ptr_host[ids]).sum()))
 
+    def node_offsets_host(self, graph_ids_host):
+        """Host copy of the collated batch's node_off [B+1] (what mask_atoms needs to size its outputs without a sync)."""
+        ids = np.asarray(graph_ids_host, dtype=np.int64)
+        return np.concatenate([[0], np.cumsum(self.node_ptr_host[ids + 1] - self.node_ptr_host[ids])]).astype(np.int64)
+
     def collate(self, graph_ids_host, graph_ids_dev=None):
         """-> namespace(x [N,2], edge_index [2,E], edge_attr [E,2], batch [N], node_off [B+1], edge_off [B+1], num_graphs),
         int64 CUDA tensors exactly as BatchMasking.from_data_list([dataset[i] for i in ids]) would hold them."""
@@ -75,6 +80,116 @@ class MoleculeStore:
                                     self.num_edges, self.edge_attr.data_ptr(), graph_ids_dev.data_ptr(), B, out.node_off.data_ptr(),
                                     out.edge_off.data_ptr(), out.x.data_ptr(), out.edge_index.data_ptr(), out.edge_attr.data_ptr(),
                                     out.batch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pgnn_collate_chem")
+        return out
+
+
+def mask_atoms(batch, node_off_host, mask_rate=0.15, seed=0, num_atom_type=119):
+    """MaskAtom (chem/util.py:189-241, mask_edge=False) on a batch collated by MoleculeStore.collate, on the device: adds
+    `masked_atom_indices` [M], `mask_node_label` [M,2], `mask_off` [B+1] to `batch` and overwrites the masked rows of
+    `batch.x` with [num_atom_type, 0].  `node_off_host`: host copy of batch.node_off (np.int64 [B+1]; from
+    MoleculeStore.node_offsets_host(ids), no device sync).  `seed`: a fresh value per step (the draw is a pure function of it)."""
+    import ctypes
+    off = np.ascontiguousarray(node_off_host, dtype=np.int64)
+    B = len(off) - 1
+    M = int(check(lib.pgnn_mask_atoms_count(off.ctypes.data_as(ctypes.c_void_p), B, float(mask_rate)), "pgnn_mask_atoms_count"))
+    dev = batch.x.device
+    i64 = dict(dtype=torch.int64, device=dev)
+    batch.masked_atom_indices, batch.mask_node_label = torch.empty((M,), **i64), torch.empty((M, 2), **i64)
+    batch.mask_off = torch.empty((B + 1,), **i64)
+    check(lib.pgnn_mask_atoms(batch.x.data_ptr(), batch.node_off.data_ptr(), B, float(mask_rate), int(num_atom_type), int(seed) & ((1 << 63) - 1),
+                              batch.mask_off.data_ptr(), batch.masked_atom_indices.data_ptr(), batch.mask_node_label.data_ptr(),
+                              torch.cuda.current_stream(dev).cuda_stream), "pgnn_mask_atoms")
+    return batch
+
+
+class IndexLists:
+    """Per-graph lists of graph-local node ids held in HBM (list_ptr [G+1] int64, values int32): the centre node of a
+    substructure, the overlap nodes of a context graph, a PPI ego graph's centre node."""
+
+    def __init__(self, lists, device="cuda"):
+        lens = np.array([0] + [len(l) for l in lists], dtype=np.int64)
+        self.ptr_host = np.cumsum(lens)
+        vals = np.concatenate([np.asarray(l, dtype=np.int32) for l in lists]) if len(lists) and self.ptr_host[-1] else np.zeros(0, np.int32)
+        self.device = torch.device(device)
+        self.ptr = torch.from_numpy(self.ptr_host).to(self.device)
+        self.values = torch.from_numpy(np.ascontiguousarray(vals, dtype=np.int32)).to(self.device)
+
+    def collate(self, ids_host, ids_dev, add=None, want_seg=False, want_sizes=False):
+        """-> (out [K], seg [K] | None, sizes [B] | None): entries offset by add[i] (a device int64 [>= B] tensor, e.g. node_off)."""
+        ids = np.asarray(ids_host, dtype=np.int64)
+        B, K = len(ids), int((self.ptr_host[ids + 1] - self.ptr_host[ids]).sum())
+        i64 = dict(dtype=torch.int64, device=self.device)
+        out, off = torch.empty((K,), **i64), torch.empty((B + 1,), **i64)
+        seg = torch.empty((K,), **i64) if want_seg else None
+        sizes = torch.empty((B,), **i64) if want_sizes else None
+        p = lambda t: None if t is None else t.data_ptr()
+        check(lib.pgnn_collate_lists(self.ptr.data_ptr(), self.values.data_ptr(), ids_dev.data_ptr(), B, p(add), off.data_ptr(), out.data_ptr(),
+                                     p(seg), p(sizes), torch.cuda.current_stream(self.device).cuda_stream), "pgnn_collate_lists")
+        return out, seg, sizes
+
+
+class SubstructContextStore:
+    """Pre-extracted (substructure, context) graph pairs in HBM and BatchSubstructContext.from_data_list on the device
+    (chem/batch.py:141-210): two molecule stores plus the centre / overlap index lists of every pair."""
+
+    def __init__(self, substruct: "MoleculeStore", context: "MoleculeStore", center_idx, overlap_idx):
+        self.substruct, self.context = substruct, context
+        dev = substruct.device
+        self.center = IndexLists([[int(c)] for c in center_idx], dev)
+        self.overlap = IndexLists(overlap_idx, dev)
+
+    def collate(self, graph_ids_host):
+        ids = np.ascontiguousarray(graph_ids_host, dtype=np.int64)
+        ids_dev = torch.from_numpy(ids).to(self.substruct.device, non_blocking=True)
+        s = self.substruct.collate(ids, ids_dev)
+        c = self.context.collate(ids, ids_dev)
+        center, _, _ = self.center.collate(ids, ids_dev, add=s.node_off)
+        overlap, seg, sizes = self.overlap.collate(ids, ids_dev, add=c.node_off, want_seg=True, want_sizes=True)
+        return SimpleNamespace(x_substruct=s.x, edge_index_substruct=s.edge_index, edge_attr_substruct=s.edge_attr, center_substruct_idx=center,
+                               x_context=c.x, edge_index_context=c.edge_index, edge_attr_context=c.edge_attr,
+                               overlap_context_substruct_idx=overlap, batch_overlapped_context=seg, overlapped_context_size=sizes,
+                               num_graphs=len(ids))
+
+
+class BioGraphStore:
+    """PPI ego graphs in HBM (node counts, int32 graph-local edge_index, the 9 binary edge attributes packed into a uint16)
+    and bio/batch.py:17-50 on the device: x [N,1] float ones, edge_index + node offset, edge_attr [E,9] float, batch,
+    center_node_idx + node offset."""
+
+    def __init__(self, num_nodes, edge_index_list, edge_attr_list, center_idx, device="cuda"):
+        n = np.array([0] + [int(v) for v in num_nodes], dtype=np.int64)
+        e = np.array([0] + [int(ei.shape[1]) for ei in edge_index_list], dtype=np.int64)
+        self.node_ptr_host, self.edge_ptr_host = np.cumsum(n), np.cumsum(e)
+        self.num_graphs, self.num_edges = len(num_nodes), int(self.edge_ptr_host[-1])
+        self.device = torch.device(device)
+        ei = np.concatenate([np.asarray(a, dtype=np.int32) for a in edge_index_list], axis=1) if self.num_edges else np.zeros((2, 0), np.int32)
+        ea = np.concatenate([np.asarray(a) for a in edge_attr_list], axis=0) if self.num_edges else np.zeros((0, 9))
+        if ea.size and not np.isin(ea, (0, 1)).all():
+            raise ValueError("bio edge attributes must be 0/1 (bio/loader.py:57-75)")
+        bits = (ea.astype(np.uint16) << np.arange(9, dtype=np.uint16)).sum(axis=1).astype(np.uint16)
+        dev = self.device
+        self.node_ptr, self.edge_ptr = torch.from_numpy(self.node_ptr_host).to(dev), torch.from_numpy(self.edge_ptr_host).to(dev)
+        self.edge_index = torch.from_numpy(np.ascontiguousarray(ei)).to(dev)
+        self.edge_bits = torch.from_numpy(bits.view(np.int16).copy()).to(dev)   # same 16 bits; torch has no uint16 arithmetic we need
+        self.center = IndexLists([[int(c)] for c in center_idx], dev)
+
+    def collate(self, graph_ids_host):
+        ids = np.ascontiguousarray(graph_ids_host, dtype=np.int64)
+        if ids.size and (ids.min() < 0 or ids.max() >= self.num_graphs):
+            raise IndexError("graph id out of range")
+        N = int((self.node_ptr_host[ids + 1] - self.node_ptr_host[ids]).sum())
+        E = int((self.edge_ptr_host[ids + 1] - self.edge_ptr_host[ids]).sum())
+        B, dev = len(ids), self.device
+        ids_dev = torch.from_numpy(ids).to(dev, non_blocking=True)
+        i64, f32 = dict(dtype=torch.int64, device=dev), dict(dtype=torch.float32, device=dev)
+        out = SimpleNamespace(x=torch.empty((N, 1), **f32), edge_index=torch.empty((2, E), **i64), edge_attr=torch.empty((E, 9), **f32),
+                              batch=torch.empty((N,), **i64), node_off=torch.empty((B + 1,), **i64), edge_off=torch.empty((B + 1,), **i64),
+                              num_graphs=B)
+        check(lib.pgnn_collate_bio(self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.edge_index.data_ptr(), self.num_edges,
+                                   self.edge_bits.data_ptr(), ids_dev.data_ptr(), B, out.node_off.data_ptr(), out.edge_off.data_ptr(),
+                                   out.x.data_ptr(), out.edge_index.data_ptr(), out.edge_attr.data_ptr(), out.batch.data_ptr(),
+                                   torch.cuda.current_stream(dev).cuda_stream), "pgnn_collate_bio")
+        out.center_node_idx, _, _ = self.center.collate(ids, ids_dev, add=out.node_off)
         return out
 
 

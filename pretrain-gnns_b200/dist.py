@@ -188,6 +188,9 @@ class GradAllReducer:
         if self.params:
             _pack(self.views, self.params)
         self.p2p.run(inv if self.scale else 1.0)
+        for src in self.flat_sources:
+            if hasattr(src, "step_done"):
+                src.step_done()   # every backward of this step has run: no forward is awaiting one any more
         for fn in after:
             fn()
         if self.params:
@@ -262,5 +265,10 @@ def encoder_flat_source(gnn):
             if buffer is not None and buffer.numel() != plan.total:
                 raise ValueError("bound gradient buffer does not match the encoder's flat layout")
             plan.grad_buffer = buffer
+    def step_done():
+        plan = gnn._fused_plan()
+        if plan is not None:
+            plan.live_forwards = 0
     src.bind = bind
+    src.step_done = step_done
     return src

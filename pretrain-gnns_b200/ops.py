@@ -34,6 +34,29 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+DEVICE_ERROR_BITS = {1: "node / segment id out of range (edge_index, batch)", 2: "atom code out of range (x)",
+                     4: "bond code out of range (edge_attr)", 8: "class label out of range", 16: "gather index out of range"}
+
+
+def device_errors(clear=True):
+    """Names of the index-range violations the kernels of the current device have flagged so far (synchronises the device;
+    include/pgnn_b200.h, PGNN_DEVERR_*).  The offending elements were dropped or clamped, never dereferenced."""
+    bits = check(lib.pgnn_device_error_flags(int(clear)), "device_error_flags")
+    return [name for bit, name in DEVICE_ERROR_BITS.items() if bits & bit]
+
+
+def raise_on_device_errors():
+    """The reference's torch index ops raise a device-side assert on an out-of-range index; call this wherever the host
+    synchronises anyway (after reading the loss) to get the same diagnosis.  PGNN_VALIDATE=1 calls it after every graph
+    preparation / embedding / loss op (one device synchronisation each: debugging only)."""
+    errs = device_errors(clear=True)
+    if errs:
+        raise PgnnError("out-of-range indices reached the kernels: " + "; ".join(errs))
+
+
+_VALIDATE = os.environ.get("PGNN_VALIDATE", "") == "1"
+
+
 def _st():
     return torch.cuda.current_stream().cuda_stream
 
@@ -79,6 +102,8 @@ class Graph:
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         check(lib.pgnn_graph_prep(_p(ei), e, n, _p(self.rowptr_t), _p(self.nbr_t), _p(self.eid_t), _p(self.rowptr_s),
                                   _p(self.nbr_s), _p(self.eid_s), _p(ws), wsb, _st()), "graph_prep")
+        if _VALIDATE:
+            raise_on_device_errors()
         self._dinv = None
         self._summaries = {}
 
@@ -111,6 +136,8 @@ class Graph:
             check(lib.pgnn_bio_edge_summary(_p(ea), _p(self.rowptr_t), _p(self.nbr_t), _p(self.eid_t), self.n, mode,
                                             _p(dinv), _p(S), _st()), "bio_edge_summary")
         self._summaries[key] = (edge_attr, edge_attr._version, S)
+        if _VALIDATE:
+            raise_on_device_errors()
         return S
 
 
@@ -376,8 +403,10 @@ class _ChemEmbed(Function):
         x, t1, t2 = x.contiguous(), _f32(t1).contiguous(), _f32(t2).contiguous()
         n, C = x.shape[0], t1.shape[1]
         out = torch.empty(n, C, dtype=torch.float32, device=x.device)
-        check(lib.pgnn_chem_embed_fwd(_p(x), _p(t1), _p(t2), n, C, _p(out), C, _st()), "chem_embed_fwd")
+        check(lib.pgnn_chem_embed_fwd(_p(x), _p(t1), t1.shape[0], _p(t2), t2.shape[0], n, C, _p(out), C, _st()), "chem_embed_fwd")
         ctx.x, ctx.shapes = x, (t1.shape[0], t2.shape[0], C)
+        if _VALIDATE:
+            raise_on_device_errors()
         return out
 
     @staticmethod
@@ -465,8 +494,10 @@ class _RowGather(Function):
             raise PgnnError("gather indices must be int64")
         m, C = idx.shape[0], x.shape[1]
         out = torch.empty(m, C, dtype=torch.float32, device=x.device)
-        check(lib.pgnn_row_gather_fwd(_p(x), x.stride(0), _p(idx), _p(idx2), m, C, _p(out), C, _st()), "row_gather_fwd")
+        check(lib.pgnn_row_gather_fwd(_p(x), x.stride(0), x.shape[0], _p(idx), _p(idx2), m, C, _p(out), C, _st()), "row_gather_fwd")
         ctx.idx, ctx.idx2, ctx.shape = idx, idx2, tuple(x.shape)
+        if _VALIDATE:
+            raise_on_device_errors()
         return out
 
     @staticmethod
@@ -474,7 +505,7 @@ class _RowGather(Function):
         g = _f32(g)
         n, C = ctx.shape
         gx = torch.zeros(n, C, dtype=torch.float32, device=g.device)
-        check(lib.pgnn_row_gather_bwd(_p(g), g.stride(0), _p(ctx.idx), _p(ctx.idx2), ctx.idx.shape[0], C, _p(gx), C, _st()),
+        check(lib.pgnn_row_gather_bwd(_p(g), g.stride(0), _p(ctx.idx), _p(ctx.idx2), ctx.idx.shape[0], C, _p(gx), C, n, _st()),
               "row_gather_bwd")
         return gx, None, None
 
@@ -639,6 +670,11 @@ class ChemGinPlan:
         # optional caller-owned destination ([total] fp32, e.g. a slice of NVLink-symmetric memory): used instead of a fresh
         # buffer whenever no parameter still holds a gradient (autograd would otherwise add a view of the buffer to itself)
         self.grad_buffer = None
+        # forwards of this module that still await their backward.  The shared grad_buffer is handed out only when exactly
+        # one is live: with two forwards in one autograd graph both backward nodes would see `p.grad is None` and the second
+        # would overwrite the buffer whose views the engine still holds as the first node's gradients.  (A forward whose
+        # graph is dropped without a backward leaves the count raised: the fresh-buffer path is then taken, which is safe.)
+        self.live_forwards = 0
 
 
 class _ChemGinEncoder(Function):
@@ -672,6 +708,10 @@ class _ChemGinEncoder(Function):
                                         float(bns[0].eps), _precision, _p(out), D, _p(ws), wsb, _st()), "chem_gin_forward")
         ctx.plan, ctx.ws, ctx.wsb, ctx.ptrs, ctx.x, ctx.dims, ctx.training = plan, ws, wsb, ptrs, x, (N, E, L, D), training
         ctx.keep = params  # the pointer table refers to these storages
+        if training and any(ctx.needs_input_grad[5:]):
+            plan.live_forwards += 1
+        if _VALIDATE:
+            raise_on_device_errors()
         return out
 
     @staticmethod
@@ -681,7 +721,9 @@ class _ChemGinEncoder(Function):
         plan = ctx.plan
         N, E, L, D = ctx.dims
         g = _f32(g)
-        if plan.grad_buffer is not None and all(p.grad is None for p in plan.params):
+        sole = plan.live_forwards == 1
+        plan.live_forwards = max(plan.live_forwards - 1, 0)
+        if plan.grad_buffer is not None and sole and all(p.grad is None for p in plan.params):
             flat = plan.grad_buffer
         else:
             flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
@@ -694,6 +736,107 @@ class _ChemGinEncoder(Function):
 
 def chem_gin_encoder(plan: ChemGinPlan, x, edge_index, edge_attr, training: bool):
     return _ChemGinEncoder.apply(plan, x, edge_index, edge_attr, training, *plan.params)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-encoder fast path: chem GCN / GraphSAGE / GAT (pgnn_chem_conv_forward / pgnn_chem_conv_backward)
+# ------------------------------------------------------------------------------------------------
+CONV_TYPE = {"gcn": 1, "graphsage": 2, "gat": 3}
+
+
+class ChemConvPlan:
+    """Same bookkeeping as ChemGinPlan for gnn_type = gcn | graphsage | gat (parameter order of include/pgnn_b200.h)."""
+
+    def __init__(self, gnn, gnn_type):
+        self.conv = CONV_TYPE[gnn_type]
+        self.L = len(gnn.gnns)
+        self.D = gnn.x_embedding1.weight.shape[1]
+        ps = [gnn.x_embedding1.weight, gnn.x_embedding2.weight]
+        for conv, bn in zip(gnn.gnns, gnn.batch_norms):
+            if gnn_type == "gat":
+                ps += [conv.weight_linear.weight, conv.weight_linear.bias, conv.att, conv.bias]
+            else:
+                ps += [conv.linear.weight, conv.linear.bias]
+            ps += [conv.edge_embedding1.weight, conv.edge_embedding2.weight, bn.weight, bn.bias]
+        self.params = ps
+        n = len(ps)
+        assert n == lib.pgnn_chem_conv_num_params(self.conv, self.L)
+        off = (_ct.c_int64 * (n + 1))()
+        check(lib.pgnn_chem_conv_grad_offsets(self.conv, self.L, self.D, off), "chem_conv_grad_offsets")
+        self.offsets = list(off)
+        self.sizes = [self.offsets[i + 1] - self.offsets[i] for i in range(n)]
+        self.shapes = [tuple(p.shape) for p in ps]
+        for p, s in zip(ps, self.sizes):
+            if p.numel() != s:
+                raise PgnnError("parameter shape does not match the chem %s layout (emb_dim / heads / vocabulary sizes)" % gnn_type)
+        self.total = self.offsets[-1]
+        self.PtrArr = _ct.c_void_p * n
+        self.BnArr = _ct.c_void_p * self.L
+        self.bns = list(gnn.batch_norms)
+        self.last_flat_grad = None
+        self.grad_buffer = None
+        self.live_forwards = 0
+
+
+class _ChemConvEncoder(Function):
+    @staticmethod
+    def forward(ctx, plan, x, edge_index, edge_attr, training, *params):
+        _dev(x, edge_index, edge_attr, *params)
+        if x.dtype != torch.int64 or x.dim() != 2 or x.shape[1] != 2:
+            raise PgnnError("chem node features must be int64 [N, 2]")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise PgnnError("edge_index must be int64 [2, E]")
+        x, ei, ea = x.contiguous(), edge_index.contiguous(), edge_attr.contiguous()
+        N, E, L, D = x.shape[0], ei.shape[1], plan.L, plan.D
+        if ea.dtype != torch.int64 or tuple(ea.shape) != (E, 2):
+            raise PgnnError("chem edge_attr must be int64 [E, 2]")
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise PgnnError("the fused encoder needs contiguous fp32 parameters")
+        if training and N == 0:
+            raise PgnnError("BatchNorm in training mode needs at least one node")
+        dev = x.device
+        ptrs = plan.PtrArr(*[p.data_ptr() for p in params])
+        bns = plan.bns
+        rm = plan.BnArr(*[b.running_mean.data_ptr() for b in bns])
+        rv = plan.BnArr(*[b.running_var.data_ptr() for b in bns])
+        nbt = plan.BnArr(*[b.num_batches_tracked.data_ptr() for b in bns])
+        wsb = lib.pgnn_chem_conv_workspace_bytes(plan.conv, N, E, L, D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        out = torch.empty(N, D, dtype=torch.float32, device=dev)
+        mom = bns[0].momentum if bns[0].momentum is not None else 0.1
+        check(lib.pgnn_chem_conv_forward(plan.conv, ptrs, rm, rv, nbt, _p(x), _p(ei), _p(ea), N, E, L, D, int(training), float(mom),
+                                         float(bns[0].eps), _precision, _p(out), D, _p(ws), wsb, _st()), "chem_conv_forward")
+        ctx.plan, ctx.ws, ctx.wsb, ctx.ptrs, ctx.x, ctx.ea, ctx.dims, ctx.training = plan, ws, wsb, ptrs, x, ea, (N, E, L, D), training
+        ctx.keep = params
+        if training and any(ctx.needs_input_grad[5:]):
+            plan.live_forwards += 1
+        if _VALIDATE:
+            raise_on_device_errors()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.training:
+            raise PgnnError("backward through the eval-mode encoder is not implemented (SURVEY.md section 3.3)")
+        plan = ctx.plan
+        N, E, L, D = ctx.dims
+        g = _f32(g)
+        sole = plan.live_forwards == 1
+        plan.live_forwards = max(plan.live_forwards - 1, 0)
+        if plan.grad_buffer is not None and sole and all(p.grad is None for p in plan.params):
+            flat = plan.grad_buffer
+        else:
+            flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
+        check(lib.pgnn_chem_conv_backward(plan.conv, ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), _p(ctx.ea), N, E, L, D, _precision, _p(flat),
+                                          _p(ctx.ws), ctx.wsb, _st()), "chem_conv_backward")
+        plan.last_flat_grad = flat
+        grads = [v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)]
+        return (None, None, None, None, None) + tuple(gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[5:]))
+
+
+def chem_conv_encoder(plan: ChemConvPlan, x, edge_index, edge_attr, training: bool):
+    return _ChemConvEncoder.apply(plan, x, edge_index, edge_attr, training, *plan.params)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -716,7 +859,7 @@ class _MaskedCE(Function):
         ldv = _pad4(V)  # 16-byte aligned logit rows: the TMA boxes of the backward GEMMs zero-fill the ragged class extent
         dev = rep.device
         rows = torch.empty(M, D, dtype=torch.float32, device=dev)
-        check(lib.pgnn_row_gather_fwd(_p(rep), rep.stride(0), _p(idx), _p(idx2), M, D, _p(rows), D, _st()), "row_gather_fwd")
+        check(lib.pgnn_row_gather_fwd(_p(rep), rep.stride(0), rep.shape[0], _p(idx), _p(idx2), M, D, _p(rows), D, _st()), "row_gather_fwd")
         logits = torch.empty(M, ldv, dtype=torch.float32, device=dev)
         check(lib.pgnn_linear_fwd(_p(rows), D, _p(w), _p(bias), M, V, D, 0, _p(logits), ldv, _precision, _st()), "linear_fwd")
         loss = torch.empty((), dtype=torch.float64, device=dev)
@@ -727,6 +870,8 @@ class _MaskedCE(Function):
         ctx.dims = (tuple(rep.shape), M, D, V, ldv, bias is not None)
         ctx.logits = logits[:, :V]
         ctx.mark_non_differentiable(ctx.logits)
+        if _VALIDATE:
+            raise_on_device_errors()
         return loss, ctx.logits
 
     @staticmethod
@@ -743,7 +888,7 @@ class _MaskedCE(Function):
             drows = torch.empty(M, D, dtype=torch.float32, device=dev)
             check(lib.pgnn_linear_bwd_x(_p(dl), ldv, _p(w), M, V, D, None, 0, _p(drows), D, _precision, _st()), "linear_bwd_x")
             grep = torch.zeros(n, D, dtype=torch.float32, device=dev)
-            check(lib.pgnn_row_gather_bwd(_p(drows), D, _p(idx), _p(ctx.idx2), M, D, _p(grep), D, _st()), "row_gather_bwd")
+            check(lib.pgnn_row_gather_bwd(_p(drows), D, _p(idx), _p(ctx.idx2), M, D, _p(grep), D, n, _st()), "row_gather_bwd")
         return grep, None, None, gw, gb, None
 
 

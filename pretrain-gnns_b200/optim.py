@@ -31,6 +31,10 @@ def chunk_table(ptrs, numels, chunk=_CHUNK):
 class Adam:
     """torch.optim.Adam(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) with one kernel launch per step.
 
+    `params` is an iterable of tensors or of param-group dicts with per-group overrides, as chem/finetune.py:180-185 passes
+    (`{"params": ..., "lr": lr * lr_scale}` for the head): one launch per group.  Step counts are kept per tensor like
+    torch's `state[p]["step"]` (a parameter that receives no gradient on some step keeps its own bias correction); tensors
+    of a group whose counts differ are stepped by separate launches.
     `grad_scale` multiplies every gradient as it is read (1/world_size turns an all-reduced SUM into the mean for free).
     `legacy_eps=True` reproduces torch 1.0.1's placement of eps (the version the reference pins, requirements.txt:2)."""
 
@@ -38,16 +42,37 @@ class Adam:
         params = list(params)
         if not params:
             raise ValueError("optimizer got an empty parameter list")
-        if lr < 0.0 or eps < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or weight_decay < 0.0:
-            raise ValueError("Invalid Adam hyper-parameter")
-        for p in params:
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        groups = params if isinstance(params[0], dict) else [dict(params=params)]
+        self.param_groups = []
+        for g in groups:
+            if not isinstance(g, dict) or "params" not in g:
+                raise TypeError("params must be an iterable of tensors or of dicts with a 'params' entry")
+            ps = g["params"]
+            ps = [ps] if torch.is_tensor(ps) else list(ps)
+            grp = dict(defaults)
+            grp.update({k: (tuple(v) if k == "betas" else v) for k, v in g.items() if k != "params"})
+            grp["params"] = ps
+            if (grp["lr"] < 0.0 or grp["eps"] < 0.0 or not 0.0 <= grp["betas"][0] < 1.0 or not 0.0 <= grp["betas"][1] < 1.0
+                    or grp["weight_decay"] < 0.0):
+                raise ValueError("Invalid Adam hyper-parameter")
+            self.param_groups.append(grp)
+        flat = [p for g in self.param_groups for p in g["params"]]
+        if not flat:
+            raise ValueError("optimizer got an empty parameter list")
+        if len({id(p) for p in flat}) != len(flat):
+            raise ValueError("some parameters appear in more than one parameter group")
+        for p in flat:
+            if not torch.is_tensor(p):
+                raise TypeError("optimizer can only optimize Tensors, but one of the params is " + type(p).__name__)
             if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
                 raise ValueError("pretrain_gnns_b200.optim.Adam needs contiguous fp32 CUDA parameters")
-        self.param_groups = [dict(params=params, lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)]
         self.grad_scale, self.legacy_eps = float(grad_scale), bool(legacy_eps)
-        self._step = 0
-        dev = params[0].device
-        sizes = [p.numel() for p in params]
+        self._params = flat
+        self._group_of = [gi for gi, g in enumerate(self.param_groups) for _ in g["params"]]
+        self._steps = [0] * len(flat)
+        dev = flat[0].device
+        sizes = [p.numel() for p in flat]
         # each tensor's slice starts on a 16-byte boundary so the kernel's float4 path applies
         starts, tot = [], 0
         for n in sizes:
@@ -59,16 +84,18 @@ class Adam:
         self._tables = {}
 
     # ---- torch.optim.Optimizer surface -----------------------------------------------------------------------------
+    def _state_of(self, i, clone=False):
+        s, n = self._slices[i]
+        p = self._params[i]
+        m, v = self._m[s:s + n].view_as(p), self._v[s:s + n].view_as(p)
+        return dict(step=torch.tensor(float(self._steps[i])), exp_avg=m.clone() if clone else m, exp_avg_sq=v.clone() if clone else v)
+
     @property
     def state(self):
-        out = {}
-        for p, (s, n) in zip(self.param_groups[0]["params"], self._slices):
-            out[p] = dict(step=torch.tensor(float(self._step)), exp_avg=self._m[s:s + n].view_as(p),
-                          exp_avg_sq=self._v[s:s + n].view_as(p))
-        return out
+        return {p: self._state_of(i) for i, p in enumerate(self._params)}
 
     def zero_grad(self, set_to_none=True):
-        for p in self.param_groups[0]["params"]:
+        for p in self._params:
             if p.grad is not None:
                 if set_to_none:
                     p.grad = None
@@ -77,41 +104,43 @@ class Adam:
                     p.grad.zero_()
 
     def state_dict(self):
-        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
-        g["params"] = list(range(len(self._slices)))
-        st = {}
-        if self._step:
-            for i, (s, n) in enumerate(self._slices):
-                p = self.param_groups[0]["params"][i]
-                st[i] = dict(step=torch.tensor(float(self._step)), exp_avg=self._m[s:s + n].view_as(p).clone(),
-                             exp_avg_sq=self._v[s:s + n].view_as(p).clone())
-        return dict(state=st, param_groups=[g])
+        groups, at = [], 0
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = list(range(at, at + len(g["params"])))
+            at += len(g["params"])
+            groups.append(d)
+        st = {i: self._state_of(i, clone=True) for i in range(len(self._params)) if self._steps[i]}
+        return dict(state=st, param_groups=groups)
 
     def load_state_dict(self, sd):
-        g = sd["param_groups"][0]
-        for k in ("lr", "betas", "eps", "weight_decay"):
-            if k in g:
-                self.param_groups[0][k] = tuple(g[k]) if k == "betas" else g[k]
-        steps = set()
+        if len(sd["param_groups"]) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        for mine, g in zip(self.param_groups, sd["param_groups"]):
+            if len(g["params"]) != len(mine["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            for k in ("lr", "betas", "eps", "weight_decay"):
+                if k in g:
+                    mine[k] = tuple(g[k]) if k == "betas" else g[k]
+        self._steps = [0] * len(self._params)
+        self._m.zero_()
+        self._v.zero_()
         for i, st in sd["state"].items():
             s, n = self._slices[int(i)]
             self._m[s:s + n].copy_(st["exp_avg"].reshape(-1))
             self._v[s:s + n].copy_(st["exp_avg_sq"].reshape(-1))
-            steps.add(int(float(st["step"])))
-        if len(steps) > 1:
-            raise ValueError("per-parameter step counts differ; this optimizer keeps one")
-        self._step = steps.pop() if steps else 0
+            self._steps[int(i)] = int(float(st["step"]))
 
     # ---- the step ---------------------------------------------------------------------------------------------------
     def _table(self, live):
-        key = tuple((i, p.data_ptr(), p.grad.data_ptr()) for i, p in live)
+        key = tuple((i, self._params[i].data_ptr(), self._params[i].grad.data_ptr()) for i in live)
         tab = self._tables.get(key)
         if tab is None:
             if len(self._tables) > 16:
                 self._tables.clear()
             mb, vb = self._m.data_ptr(), self._v.data_ptr()
-            host = chunk_table([(p.data_ptr(), p.grad.data_ptr(), mb + 4 * self._slices[i][0], vb + 4 * self._slices[i][0])
-                                for i, p in live], [p.numel() for _, p in live])
+            host = chunk_table([(self._params[i].data_ptr(), self._params[i].grad.data_ptr(), mb + 4 * self._slices[i][0],
+                                 vb + 4 * self._slices[i][0]) for i in live], [self._params[i].numel() for i in live])
             dev = torch.from_numpy(host.view(np.uint8).copy()).to(self._m.device)
             tab = (dev, len(host))
             self._tables[key] = tab
@@ -123,19 +152,18 @@ class Adam:
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        g = self.param_groups[0]
-        live = []
-        for i, p in enumerate(g["params"]):
+        launches = {}  # (group, step count after this update) -> tensor indices
+        for i, p in enumerate(self._params):
             if p.grad is None:
                 continue
             if p.grad.dtype != torch.float32 or not p.grad.is_contiguous() or p.grad.device != p.device:
                 raise ValueError("gradients must be contiguous fp32 tensors on the parameter's device")
-            live.append((i, p))
-        if not live:
-            return loss
-        self._step += 1
-        dev, n = self._table(live)
-        check(lib.pgnn_adam_step(dev.data_ptr(), n, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
-                                 self.grad_scale, self._step, int(self.legacy_eps),
-                                 torch.cuda.current_stream(self._m.device).cuda_stream), "pgnn_adam_step")
+            self._steps[i] += 1
+            launches.setdefault((self._group_of[i], self._steps[i]), []).append(i)
+        st = torch.cuda.current_stream(self._m.device).cuda_stream
+        for (gi, step), live in launches.items():
+            g = self.param_groups[gi]
+            dev, n = self._table(tuple(live))
+            check(lib.pgnn_adam_step(dev.data_ptr(), n, g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
+                                     self.grad_scale, step, int(self.legacy_eps), st), "pgnn_adam_step")
         return loss

@@ -89,6 +89,32 @@ def test_fused_and_layerwise_gin_paths_agree():
     assert torch.allclose(e1, e2, atol=2e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("t", ["gcn", "graphsage", "gat"])
+def test_fused_and_layerwise_conv_paths_agree(t):
+    """pgnn_chem_conv_* (one call per pass) against the layer-by-layer composition of the same C-ABI operators
+    (model.fused = False): same kernels in the same order, so outputs, gradients and BatchNorm state agree to rounding."""
+    b = syn.one_direction_only(syn.zinc_batch(32, 100), 5)
+    P = O.make_params("chem", t, 5, 300, seed=21)
+    R = probe((b["x"].shape[0], 300), 5).to(DEV)
+    res = []
+    for fused in (True, False):
+        model, out = _run("chem", t, b, P, True, fused=fused)
+        assert (model._fused_plan() is not None) == fused
+        (out * R).sum().backward()
+        res.append((out.detach(), {k: p.grad for k, p in model.named_parameters()}, model.state_dict()))
+    assert torch.allclose(res[0][0], res[1][0], atol=2e-5, rtol=1e-5)
+    gmax = max(float(g.abs().max()) for g in res[1][1].values())
+    for k, g in res[1][1].items():
+        scale = max(float(g.abs().max()), 1e-3 * gmax)
+        assert float((res[0][1][k] - g).abs().max()) <= 2e-4 * scale, k
+    for k in res[0][2]:
+        assert torch.allclose(res[0][2][k].float(), res[1][2][k].float(), atol=1e-5, rtol=1e-5), k
+    with torch.no_grad():
+        _, e1 = _run("chem", t, b, P, False, fused=True)
+        _, e2 = _run("chem", t, b, P, False, fused=False)
+    assert torch.allclose(e1, e2, atol=2e-5, rtol=1e-5)
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_gin_encoder_vs_oracle_both_paths(fused):
     b = syn.zinc_batch(32, 100)

@@ -278,3 +278,40 @@ def test_host_tensor_is_rejected():
     cabi = importlib.import_module("pretrain-gnns_b200._cabi")
     with pytest.raises(cabi.PgnnError):
         ops.linear(torch.zeros(2, 3), torch.zeros(4, 3), None)
+
+
+def test_out_of_range_indices_are_flagged_not_dereferenced():
+    """an out-of-range node id / atom code / bond code / label / gather index must not become a silent
+    out-of-bounds access.  The kernels drop or clamp the element and raise a PGNN_DEVERR_* bit (include/pgnn_b200.h)."""
+    ops.device_errors(clear=True)
+    b = syn.zinc_batch(4, 3)
+    n = b["x"].shape[0]
+    assert ops.device_errors() == []
+    ei = b["edge_index"].clone()
+    ei[0, 5] = n + 1000           # target far outside the node range
+    ei[1, 9] = -3
+    g = ops.Graph(ei.to(DEV), n)
+    errs = ops.device_errors()
+    assert len(errs) == 1 and "node" in errs[0]
+    assert int(g.rowptr_t[-1]) == ei.shape[1] - 2 and int(g.rowptr_s[-1]) == ei.shape[1] - 2   # both bad edges dropped from both bucketings
+    assert int(g.nbr_t.max()) < n and int(g.nbr_s.max()) < n and int(g.nbr_t.min()) >= 0
+    x = b["x"].clone()
+    x[3, 0] = 500
+    t1, t2 = torch.randn(120, 300, device=DEV), torch.randn(3, 300, device=DEV)
+    out = ops.chem_embed(x.to(DEV), t1, t2)
+    assert torch.isfinite(out).all() and any("atom" in e for e in ops.device_errors())
+    ea = b["edge_attr"].clone()
+    ea[2, 0] = 77
+    g2 = ops.Graph(b["edge_index"].to(DEV), n)
+    g2.summary("chem", ops.AGG_SUM, ea.to(DEV))
+    assert any("bond" in e for e in ops.device_errors())
+    rep = torch.randn(n, 300, device=DEV)
+    rows = ops.row_gather(rep, torch.tensor([0, n + 5, 2], device=DEV))
+    assert any("gather" in e for e in ops.device_errors()) and float(rows[1].abs().max()) == 0.0
+    W, bias = torch.randn(119, 300, device=DEV) * 0.05, torch.zeros(119, device=DEV)
+    loss, _ = ops.masked_atom_loss(rep, torch.tensor([0, 1], device=DEV), torch.tensor([5, 4000], device=DEV), W, bias)
+    assert torch.isfinite(loss) and any("label" in e for e in ops.device_errors())
+    with pytest.raises(ops.PgnnError):
+        ops.Graph(ei.to(DEV), n)
+        ops.raise_on_device_errors()
+    assert ops.device_errors() == []

@@ -22,6 +22,11 @@ def _store(num, seed):
     return data.MoleculeStore.from_data_list(D, device=DEV), graphs, b
 
 
+def _store_from(graphs):
+    D = [type("D", (), dict(x=g[0], edge_index=g[1], edge_attr=g[2])) for g in graphs]
+    return data.MoleculeStore.from_data_list(D, device=DEV)
+
+
 @pytest.mark.parametrize("ids", [[3], [0, 1, 2, 3], [9, 9, 2, 0, 9], list(range(39, -1, -1)), []])
 def test_collate_bit_exact(ids):
     st, graphs, _ = _store(40, 3)
@@ -80,8 +85,7 @@ def test_adam_matches_torch(wd, scale):
         ref.step()
         mine.step()
     for i, (r, m) in enumerate(zip(ref_p, my_p)):
-        if i == 3:
-            continue  # torch keeps a per-tensor step count; this optimizer keeps one (documented), so tensor 3 differs
+        # tensor 3 is stepped once, at iteration 5: torch keeps a per-tensor step count and so does this optimizer
         err = (m.detach().cpu() - r.detach()).abs()
         assert bool((err <= 2e-6 * r.detach().abs() + 4e-7 * lr * 10).all()), (i, err.max().item())
         st = mine.state[m]
@@ -117,9 +121,27 @@ def test_adam_state_dict_roundtrip_with_torch():
     assert ref2.param_groups[0]["lr"] == 2e-3
     mine2 = optim.Adam(my_p, lr=1.0)
     mine2.load_state_dict(ref.state_dict())          # and torch's into ours
-    assert mine2._step == 2 and mine2.param_groups[0]["lr"] == 2e-3
+    assert mine2._steps == [2, 2] and mine2.param_groups[0]["lr"] == 2e-3
     for a, b in zip(my_p, t_p):
         assert torch.allclose(mine2.state[a]["exp_avg"], ref.state[b]["exp_avg"], rtol=2e-6, atol=0)
+
+
+def test_adam_param_groups_like_finetune():
+    """chem/finetune.py:180-185: param-group dicts with a per-group lr (lr * lr_scale for the prediction head)."""
+    P = _params(4, [(33, 7), (12,), (5, 5)])
+    my_p = [torch.nn.Parameter(p.clone().to(DEV)) for p in P]
+    t_p = [torch.nn.Parameter(p.clone()) for p in P]
+    groups = lambda ps: [{"params": ps[:2]}, {"params": ps[2:], "lr": 1e-3 * 7.0, "weight_decay": 0.0}]
+    mine, ref = optim.Adam(groups(my_p), lr=1e-3, weight_decay=0.01), torch.optim.Adam(groups(t_p), lr=1e-3, weight_decay=0.01)
+    for step in range(3):
+        for a, b, g in zip(my_p, t_p, _params(40 + step, [(33, 7), (12,), (5, 5)])):
+            a.grad, b.grad = g.to(DEV), g.clone()
+        mine.step(); ref.step()
+    for a, b in zip(my_p, t_p):
+        assert torch.allclose(a.detach().cpu(), b.detach(), rtol=3e-6, atol=1e-7)
+    assert [g["lr"] for g in mine.state_dict()["param_groups"]] == [1e-3, 7e-3]
+    with pytest.raises(TypeError):
+        optim.Adam([{"lr": 1.0}])
 
 
 def test_adam_steps_fused_encoder_gradients():
@@ -143,3 +165,59 @@ def test_adam_steps_fused_encoder_gradients():
         ref.step()
     for (n, a), c in zip(gnn.named_parameters(), twin):
         assert torch.allclose(a, c, rtol=2e-6, atol=1e-8), n
+
+
+def test_mask_atoms_device_vs_oracle():
+    """pgnn_mask_atoms on a device-collated batch: bit-exact against oracle/step_io_oracle.mask_atoms (which is pinned to
+    the reference's MaskAtom + BatchMasking in tests/test_oracle_vs_reference.py); B > 1024 exercises the scan's carry."""
+    for G, B, seed in ((40, 16, 7), (300, 1500, 123456789)):
+        store, graphs, _ = _store(G, 5)
+        rng = np.random.default_rng(seed)
+        ids = rng.integers(0, G, size=B)
+        batch = store.collate(ids)
+        off = store.node_offsets_host(ids)
+        ref_x, ref_idx, ref_lab, ref_off = SO.mask_atoms(batch.x.cpu().numpy(), off, 0.15, seed)
+        data.mask_atoms(batch, off, 0.15, seed)
+        assert np.array_equal(batch.node_off.cpu().numpy(), off)
+        assert np.array_equal(batch.mask_off.cpu().numpy(), ref_off)
+        assert np.array_equal(batch.masked_atom_indices.cpu().numpy(), ref_idx)
+        assert np.array_equal(batch.mask_node_label.cpu().numpy(), ref_lab)
+        assert np.array_equal(batch.x.cpu().numpy(), ref_x)
+        assert int((batch.x[:, 0] == 119).sum()) == len(ref_idx)
+
+
+def test_substruct_context_and_bio_collate_device_vs_oracle():
+    G = 24
+    sub, ctx = syn.zinc_batch(G, 61, n_lo=12, n_hi=22), syn.zinc_batch(G, 62, n_lo=4, n_hi=14, tree_only=True)
+    sg, cg = syn.split_graphs(sub), syn.split_graphs(ctx)
+    rng = np.random.default_rng(5)
+    center = [int(rng.integers(0, len(g[0]))) for g in sg]
+    overlap = [sorted(rng.choice(len(g[0]), size=int(rng.integers(1, min(4, len(g[0])) + 1)), replace=False).tolist()) for g in cg]
+    st = data.SubstructContextStore(_store_from(sg), _store_from(cg), center, overlap)
+    ids = rng.integers(0, G, size=50)
+    out = st.collate(ids)
+    s, c = SO.collate_chem(sg, ids), SO.collate_chem(cg, ids)
+    cen, _, _, _ = SO.collate_lists(np.arange(G + 1), np.array(center), ids, add=s["node_off"])
+    ov, seg, sizes, _ = SO.collate_lists(np.cumsum([0] + [len(o) for o in overlap]), np.concatenate(overlap), ids, add=c["node_off"])
+    for k, v in (("x_substruct", s["x"]), ("edge_index_substruct", s["edge_index"]), ("edge_attr_substruct", s["edge_attr"]),
+                 ("center_substruct_idx", cen), ("x_context", c["x"]), ("edge_index_context", c["edge_index"]),
+                 ("edge_attr_context", c["edge_attr"]), ("overlap_context_substruct_idx", ov), ("batch_overlapped_context", seg),
+                 ("overlapped_context_size", sizes)):
+        assert np.array_equal(getattr(out, k).cpu().numpy(), v), k
+    # bio
+    pb = syn.ppi_batch(6, 9, n_lo=20, n_hi=35, num_tasks=4)
+    ptr = pb["ptr"].numpy()
+    ei, ea = pb["edge_index"].numpy(), pb["edge_attr"].numpy()
+    ea[::7, 8] = 1.0   # exercise the ninth (mask) bit as well
+    owner = np.searchsorted(ptr, ei[0], side="right") - 1
+    eptr = np.searchsorted(owner, np.arange(len(ptr)))
+    graphs = [(int(ptr[g + 1] - ptr[g]), ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]]) for g in range(6)]
+    centers = [0, 3, 1, 0, 2, 5]
+    bs = data.BioGraphStore([g[0] for g in graphs], [g[1] for g in graphs], [g[2] for g in graphs], centers)
+    ids = np.array([5, 0, 0, 3])
+    o = bs.collate(ids)
+    ref = SO.collate_bio(graphs, ids)
+    for k in ("x", "edge_index", "edge_attr", "batch", "node_off", "edge_off"):
+        assert np.array_equal(getattr(o, k).cpu().numpy(), ref[k]), k
+    cen, _, _, _ = SO.collate_lists(np.arange(7), np.array(centers), ids, add=ref["node_off"])
+    assert np.array_equal(o.center_node_idx.cpu().numpy(), cen)

@@ -159,3 +159,86 @@ def test_train_bodies_port_equals_reference(config):
         scale = gmax if zero else max(float(p.grad.abs().max()), 1e-3 * gmax)
         # same arithmetic in a different order (fp32): agreement to a few ulps of the accumulated magnitude
         assert float((L[k].grad - p.grad).abs().max()) <= 2e-4 * scale, (k, float((L[k].grad - p.grad).abs().max()) / scale)
+
+
+def test_mask_atoms_oracle_equals_reference_maskatom():
+    """oracle/step_io_oracle.mask_atoms against the reference's own MaskAtom.__call__ fed the same atom choice (its
+    `masked_atom_indices` debugging argument, chem/util.py:206,225-241) followed by BatchMasking.from_data_list."""
+    util = R.load("chem", "util")
+    batch_mod = R.load("chem", "batch")
+    from torch_geometric.data import Data
+    b = syn.zinc_batch(7, 41)
+    graphs = syn.split_graphs(b)
+    node_off = b["ptr"].numpy()
+    choice = SO.mask_atom_choice(node_off, 0.15, seed=12345)
+    assert [len(c) for c in choice] == [int(len(g[0]) * 0.15 + 1) for g in graphs]
+    t = util.MaskAtom(num_atom_type=119, num_edge_type=5, mask_rate=0.15, mask_edge=False)
+    datas = []
+    for (x, ei, ea), local in zip(graphs, choice):
+        d = Data(x=torch.from_numpy(x.copy()), edge_index=torch.from_numpy(ei.copy()), edge_attr=torch.from_numpy(ea.copy()))
+        datas.append(t(d, masked_atom_indices=list(local)))
+    ref = batch_mod.BatchMasking.from_data_list(datas)
+    x2, idx, labels, off = SO.mask_atoms(b["x"].numpy(), node_off, 0.15, seed=12345)
+    assert np.array_equal(x2, ref.x.numpy()) and np.array_equal(idx, ref.masked_atom_indices.numpy())
+    assert np.array_equal(labels, ref.mask_node_label.numpy()) and off[-1] == len(idx)
+    # the draw is a uniform k-subset: over many seeds every node of a graph is chosen about equally often
+    n0 = int(node_off[1])
+    hits = np.zeros(n0)
+    for s in range(400):
+        hits[SO.mask_atom_choice(node_off[:2], 0.15, seed=s)[0]] += 1
+    k = int(n0 * 0.15 + 1)
+    assert abs(hits.mean() - 400 * k / n0) < 1e-9 and hits.min() > 0.5 * 400 * k / n0 and hits.max() < 1.6 * 400 * k / n0
+
+
+def test_substruct_context_collate_oracle_equals_reference():
+    """chem/batch.py:141-210: BatchSubstructContext.from_data_list on per-pair Data objects vs collate_chem x 2 + collate_lists."""
+    batch_mod = R.load("chem", "batch")
+    from torch_geometric.data import Data
+    G = 6
+    sub, ctx = syn.zinc_batch(G, 51, n_lo=12, n_hi=22), syn.zinc_batch(G, 52, n_lo=4, n_hi=14, tree_only=True)
+    sg, cg = syn.split_graphs(sub), syn.split_graphs(ctx)
+    rng = np.random.default_rng(3)
+    center = [int(rng.integers(0, len(g[0]))) for g in sg]
+    overlap = [sorted(rng.choice(len(g[0]), size=int(rng.integers(1, min(4, len(g[0])) + 1)), replace=False).tolist()) for g in cg]
+    ids = [4, 1, 1, 5]
+    datas = []
+    for g in ids:
+        T = lambda a: torch.from_numpy(np.asarray(a).copy())
+        datas.append(Data(x=T(sg[g][0]), edge_index=T(sg[g][1]), edge_attr=T(sg[g][2]),   # the main graph (unused by the collator but num_nodes reads x)
+                          x_substruct=T(sg[g][0]), edge_index_substruct=T(sg[g][1]), edge_attr_substruct=T(sg[g][2]),
+                          center_substruct_idx=torch.tensor([center[g]]),
+                          x_context=T(cg[g][0]), edge_index_context=T(cg[g][1]), edge_attr_context=T(cg[g][2]),
+                          overlap_context_substruct_idx=torch.tensor(overlap[g])))
+    ref = batch_mod.BatchSubstructContext.from_data_list(datas)
+    s, c = SO.collate_chem(sg, ids), SO.collate_chem(cg, ids)
+    cptr, optr = np.arange(G + 1), np.cumsum([0] + [len(o) for o in overlap])
+    cen, _, _, _ = SO.collate_lists(cptr, np.array(center), ids, add=s["node_off"])
+    ov, seg, sizes, _ = SO.collate_lists(optr, np.concatenate(overlap), ids, add=c["node_off"])
+    for k, v in (("x_substruct", s["x"]), ("edge_index_substruct", s["edge_index"]), ("edge_attr_substruct", s["edge_attr"]),
+                 ("center_substruct_idx", cen), ("x_context", c["x"]), ("edge_index_context", c["edge_index"]),
+                 ("edge_attr_context", c["edge_attr"]), ("overlap_context_substruct_idx", ov), ("batch_overlapped_context", seg),
+                 ("overlapped_context_size", sizes)):
+        assert np.array_equal(v, ref[k].numpy()), k
+
+
+def test_bio_collate_oracle_equals_reference():
+    """bio/batch.py:17-50 (BatchFinetune.from_data_list, the collator of bio/dataloader.py's DataLoaderFinetune: edge_index
+    and center_node_idx offset by the running node count) vs collate_bio + collate_lists."""
+    batch_mod = R.load("bio", "batch")
+    from torch_geometric.data import Data
+    pb = syn.ppi_batch(5, 9, n_lo=20, n_hi=35, num_tasks=4)
+    ptr = pb["ptr"].numpy()
+    ei, ea = pb["edge_index"].numpy(), pb["edge_attr"].numpy()
+    owner = np.searchsorted(ptr, ei[0], side="right") - 1
+    eptr = np.searchsorted(owner, np.arange(len(ptr)))
+    graphs = [(int(ptr[g + 1] - ptr[g]), ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]]) for g in range(5)]
+    centers = [0, 3, 1, 0, 2]
+    ids = [2, 0, 4]
+    datas = [Data(x=torch.ones(graphs[g][0], 1), edge_index=torch.from_numpy(graphs[g][1].copy()), edge_attr=torch.from_numpy(graphs[g][2].copy()),
+                  center_node_idx=torch.tensor([centers[g]])) for g in ids]
+    ref = batch_mod.BatchFinetune.from_data_list(datas)
+    mine = SO.collate_bio(graphs, ids)
+    for k in ("x", "edge_index", "edge_attr", "batch"):
+        assert np.array_equal(mine[k], ref[k].numpy()), k
+    cen, _, _, _ = SO.collate_lists(np.arange(6), np.array(centers), ids, add=mine["node_off"])
+    assert np.array_equal(cen, ref.center_node_idx.numpy())

@@ -15,7 +15,8 @@ PKG = os.path.join(ROOT, "pretrain-gnns_b200")
 OUT = os.path.join(ROOT, "tools", "_ub")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 VARIANTS = {"full": [], "no_tma": ["-DPGNN_UB_NO_TMA"], "no_convert": ["-DPGNN_UB_NO_CONVERT"], "no_mma": ["-DPGNN_UB_NO_MMA"],
-            "no_epilogue": ["-DPGNN_UB_NO_EPILOGUE"], "mma_only": ["-DPGNN_UB_NO_TMA", "-DPGNN_UB_NO_CONVERT"]}
+            "no_epilogue": ["-DPGNN_UB_NO_EPILOGUE"], "mma_only": ["-DPGNN_UB_NO_TMA", "-DPGNN_UB_NO_CONVERT"],
+            "trace_all": ["-DPGNN_TRACE_ALL"]}
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "--expt-relaxed-constexpr"]
 
@@ -32,8 +33,20 @@ def build():
         print("built", name)
 
 
+def run_env():
+    """Envelope over ALL CTAs of the full kernel (trace_all build): earliest / latest stamp of every phase."""
+    env = dict(os.environ, PGNN_LIB=os.path.join(OUT, "libpgnn_trace_all.so"))
+    tr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "trace_env.py")], env=env, capture_output=True, text=True, timeout=180)
+    print(tr.stdout)
+    if tr.returncode:
+        print("trace_env failed:", tr.stderr[-400:])
+
+
 def run():
+    run_env()
     for name in VARIANTS:
+        if name == "trace_all":
+            continue
         env = dict(os.environ, PGNN_LIB=os.path.join(OUT, "libpgnn_%s.so" % name))
         tr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "trace_tc.py")], env=env, capture_output=True, text=True, timeout=120)
         for line in tr.stdout.splitlines():
