@@ -148,6 +148,7 @@ __device__ __forceinline__ void splitk_fold_in_kernel(const float* __restrict__ 
       if (seen >= splits) break;
       if ((it & 255u) == 255u && globaltimer_ns() - t0 > 2000000000ull) asm volatile("trap;");
     }
+    __threadfence();
   }
   asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
   const int rows_here = min(BM, M - m0);
