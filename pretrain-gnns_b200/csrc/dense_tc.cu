@@ -546,8 +546,19 @@ static bool fold_in_kernel_enabled() {
   return v == 1;
 }
 
+int pgnn_tc_linear_bwd_w_ws2(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st, bool in_kernel_fold_ok);
+
 int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st) {
+  return pgnn_tc_linear_bwd_w_ws2(gy, ldgy, x, ldx, M, N, K, gw, gb, partials, partial_floats, st, true);
+}
+
+// in_kernel_fold_ok = false: the partial tiles are folded by k_splitk_reduce.  Callers that run this GEMM CONCURRENTLY with other
+// full-chip kernels (the encoders' side stream) must pass false: CTAs of the in-kernel fold spin until all their siblings have
+// arrived, and a sibling queued behind another kernel's CTAs would keep the arrived ones idling on their SMs.
+int pgnn_tc_linear_bwd_w_ws2(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st, bool in_kernel_fold_ok) {
   if (K % 4 || ldgy % 4 || ldx % 4 || !aligned16(gy) || !aligned16(x) || !aligned16(gw) || M < 1) return PGNN_EUNSUPPORTED;
   if ((N % 4) && !tma_enabled()) return PGNN_EUNSUPPORTED;  // ragged N (e.g. 119 classes) only through the TMA boxes
   // output [N, K] (rows N = "M" of the MMA), reduction over the M node rows, split so the grid fills the chip
@@ -562,7 +573,7 @@ int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64
     // The fold runs inside the GEMM when its whole grid is resident at once (one 220 KB CTA per SM): the counters sit behind
     // the partial tiles in the workspace.
     const int64_t ctr_floats = align_up(tiles, 4);
-    const bool in_kernel = fold_in_kernel_enabled() && (int64_t)tiles * splits <= device_sm_count() && (K % 4) == 0 &&
+    const bool in_kernel = in_kernel_fold_ok && fold_in_kernel_enabled() && (int64_t)tiles * splits <= device_sm_count() && (K % 4) == 0 &&
                            partial_floats >= (int64_t)splits * N * K + ctr_floats;
     if (in_kernel) {
       unsigned int* ctr = reinterpret_cast<unsigned int*>(partials + (int64_t)splits * N * K);

@@ -10,6 +10,10 @@
 // also the buffer the data-parallel all-reduce runs on.
 #include "common.cuh"
 
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st);
 int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
@@ -26,6 +30,8 @@ int pgnn_tc_linear_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, 
 int pgnn_tc_linear_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
 int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st);
+int pgnn_tc_linear_bwd_w_ws2(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st, bool in_kernel_fold_ok);
 int64_t pgnn_tc_wgrad_workspace_floats(int64_t M, int64_t N, int64_t K);
 int pgnn_tc_linear_bwd_x_wt(const float* gy, int64_t ldgy, const float* wT, int64_t M, int64_t N, int64_t K, const float* relu_src,
                             int64_t ldr, float* gx, int64_t ldgx, cudaStream_t st, const PgnnGemmHooks* hooks);
@@ -94,8 +100,8 @@ Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.z1 = c.take<float>(L * N * 2 * D);
   w.z2 = c.take<float>(L * N * D);
   w.gh = c.take<float>(N * D);
-  w.gz2 = c.take<float>(N * D);
-  w.gz1 = c.take<float>(N * 2 * D);
+  w.gz2 = c.take<float>(2 * N * D);       // two copies each: layer l's weight-gradient GEMMs (side stream) may still read
+  w.gz1 = c.take<float>(2 * N * 2 * D);   // them while layer l-1's backward writes the other copy
   w.gaggr = c.take<float>(N * D);
   w.wT = c.take<float>(L * 4 * D * D);
   w.wpart_floats = pgnn_tc_wgrad_workspace_floats(N, 2 * D, D);  // both MLP weight gradients have 2D*D elements
@@ -111,6 +117,45 @@ Ws carve(void* base, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.scratch = c.take<char>(sb);
   w.total = c.off;
   return w;
+}
+
+// Weight-gradient GEMMs on a side stream.  Per layer the critical path of the backward is BatchNorm-bwd -> dgrad2 -> dgrad1 ->
+// transpose gather -> (next layer); wgrad2 (needs gz2, z1) and wgrad1 (needs gz1, aggr) only feed the gradient buffer.  On
+// their own stream they run under the next layer's BatchNorm sweeps and gathers (LSU / L2-bound kernels that leave the tensor
+// pipe and most of shared memory idle) instead of in front of them.  Ordering is by events; gz2 / gz1 are double-buffered
+// by layer parity so the main stream never overwrites an operand a pending wgrad still reads.  PGNN_WGRAD_STREAM=0 disables.
+struct SideCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t gz2_ready[2] = {}, gz1_ready[2] = {}, w2_done[2] = {}, w1_done[2] = {}, join = nullptr;
+  bool ok = false;
+};
+SideCtx* side_ctx(cudaStream_t main_stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SideCtx*> all;
+  static int enabled = -1;
+  std::lock_guard<std::mutex> g(mu);
+  if (enabled < 0) {
+    const char* e = getenv("PGNN_WGRAD_STREAM");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  auto key = std::make_pair(dev, main_stream);
+  auto it = all.find(key);
+  if (it != all.end()) return it->second->ok ? it->second : nullptr;
+  SideCtx* c = new SideCtx();
+  all[key] = c;
+  bool ok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&c->gz2_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->gz1_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->w2_done[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->w1_done[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  c->ok = ok;
+  return ok ? c : nullptr;
 }
 
 #define TRY(call)                 \
@@ -261,6 +306,8 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
   }
   const float* gy = g_node_rep;
   int64_t ldgy = ldg;
+  SideCtx* sc = precision == 1 ? side_ctx(st) : nullptr;
+  cudaStream_t wst = sc ? sc->side : st;   // the stream of the weight-gradient GEMMs
   for (int64_t l = L - 1; l >= 0; --l) {
     const void* const* p = params + P_LAYER0 + l * L_COUNT;
     const int64_t* o = off + P_LAYER0 + l * L_COUNT;
@@ -268,33 +315,50 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
     const float* z1 = w.z1 + l * N * 2 * D;
     const float* z2 = w.z2 + l * N * D;
     const bool last = (l == L - 1);
+    const int par = (int)(l & 1);
+    float* gz2 = w.gz2 + (sc ? par * N * D : 0);
+    float* gz1 = w.gz1 + (sc ? par * N * 2 * D : 0);
     // BatchNorm (+ReLU mask recomputed from z2) backward; the same pass leaves colsum(gz2) = gradient of mlp.2.bias
+    if (sc) PGNN_CUDA(cudaStreamWaitEvent(st, sc->w2_done[par], 0));  // layer l+2's wgrad2 has finished reading this copy
     TRY(pgnn_internal_bn_bwd_colsum(gy, ldgy, z2, D, N, D, (const float*)p[L_GAMMA], (const float*)p[L_BETA], w.mean + l * D,
-                                    w.invstd + l * D, !last, w.gz2, D, grads + o[L_GAMMA], grads + o[L_BETA], grads + o[L_B2],
+                                    w.invstd + l * D, !last, gz2, D, grads + o[L_GAMMA], grads + o[L_BETA], grads + o[L_B2],
                                     w.scratch, st));
     // MLP backward.  On the tensor path the dgrad epilogues carry the column reductions that would otherwise be
     // passes of their own: colsum(gz1) = gradient of mlp.0.bias, and S^T gaggr = gradient of the two bond tables.
     bool fused = false;
     if (precision == 1) {
-      int rc = pgnn_tc_linear_bwd_w_ws(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, w.wpart, w.wpart_floats, st);
+      if (sc) {
+        PGNN_CUDA(cudaEventRecord(sc->gz2_ready[par], st));
+        PGNN_CUDA(cudaStreamWaitEvent(wst, sc->gz2_ready[par], 0));
+      }
+      int rc = pgnn_tc_linear_bwd_w_ws2(gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, w.wpart, w.wpart_floats, wst, sc == nullptr);
       if (rc == PGNN_OK) {
+        if (sc) {
+          PGNN_CUDA(cudaEventRecord(sc->w2_done[par], wst));
+          PGNN_CUDA(cudaStreamWaitEvent(st, sc->w1_done[par], 0));  // layer l+2's wgrad1 has finished reading gz1[par]
+        }
         PGNN_CUDA(cudaMemsetAsync(grads + o[L_B1], 0, sizeof(float) * 2 * D, st));
         PgnnGemmHooks h1;
         h1.colsum = grads + o[L_B1];
-        rc = have_wT ? pgnn_tc_linear_bwd_x_wt(w.gz2, D, w.wT + (2 * l + 1) * 2 * D * D, N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1)
+        rc = have_wT ? pgnn_tc_linear_bwd_x_wt(gz2, D, w.wT + (2 * l + 1) * 2 * D * D, N, D, 2 * D, z1, 2 * D, gz1, 2 * D, st, &h1)
                      : PGNN_EUNSUPPORTED;
         if (rc == PGNN_EUNSUPPORTED)
-          rc = pgnn_tc_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, st, &h1);
+          rc = pgnn_tc_linear_bwd_x(gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, gz1, 2 * D, st, &h1);
         if (rc != PGNN_OK) return rc;
-        rc = pgnn_tc_linear_bwd_w_ws(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], nullptr, w.wpart, w.wpart_floats, st);
+        if (sc) {
+          PGNN_CUDA(cudaEventRecord(sc->gz1_ready[par], st));
+          PGNN_CUDA(cudaStreamWaitEvent(wst, sc->gz1_ready[par], 0));
+        }
+        rc = pgnn_tc_linear_bwd_w_ws2(gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], nullptr, w.wpart, w.wpart_floats, wst, sc == nullptr);
         if (rc != PGNN_OK) return rc;
+        if (sc) PGNN_CUDA(cudaEventRecord(sc->w1_done[par], wst));
         PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));  // the two tables are adjacent in the layout
         PgnnGemmHooks h2;
         h2.S = w.S; h2.Q = 9; h2.gT = grads + o[L_ET1]; h2.gT2 = grads + o[L_ET2]; h2.q_split = 6; h2.ldt = D;
-        rc = have_wT ? pgnn_tc_linear_bwd_x_wt(w.gz1, 2 * D, w.wT + (2 * l) * 2 * D * D, N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2)
+        rc = have_wT ? pgnn_tc_linear_bwd_x_wt(gz1, 2 * D, w.wT + (2 * l) * 2 * D * D, N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2)
                      : PGNN_EUNSUPPORTED;
         if (rc == PGNN_EUNSUPPORTED)
-          rc = pgnn_tc_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2);
+          rc = pgnn_tc_linear_bwd_x(gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, st, &h2);
         if (rc != PGNN_OK) return rc;
         fused = true;
       } else if (rc != PGNN_EUNSUPPORTED) {
@@ -302,10 +366,14 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
       }
     }
     if (!fused) {
-      TRY(pgnn_linear_bwd_w(w.gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, precision, stream));
-      TRY(pgnn_linear_bwd_x(w.gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, w.gz1, 2 * D, precision, stream));
-      TRY(pgnn_linear_bwd_w(w.gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], grads + o[L_B1], precision, stream));
-      TRY(pgnn_linear_bwd_x(w.gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, precision, stream));
+      if (sc) {  // an unsupported shape on the tensor path: everything on the caller's stream from here on
+        PGNN_CUDA(cudaEventRecord(sc->join, wst));
+        PGNN_CUDA(cudaStreamWaitEvent(st, sc->join, 0));
+      }
+      TRY(pgnn_linear_bwd_w(gz2, D, z1, 2 * D, N, D, 2 * D, grads + o[L_W2], nullptr, precision, stream));
+      TRY(pgnn_linear_bwd_x(gz2, D, (const float*)p[L_W2], N, D, 2 * D, z1, 2 * D, gz1, 2 * D, precision, stream));
+      TRY(pgnn_linear_bwd_w(gz1, 2 * D, aggr, D, N, 2 * D, D, grads + o[L_W1], grads + o[L_B1], precision, stream));
+      TRY(pgnn_linear_bwd_x(gz1, 2 * D, (const float*)p[L_W1], N, 2 * D, D, nullptr, 0, w.gaggr, D, precision, stream));
       // bond tables: gT = S^T gaggr, rows 0..5 -> edge_embedding1, 6..8 -> edge_embedding2
       PGNN_CUDA(cudaMemsetAsync(grads + o[L_ET1], 0, sizeof(float) * 9 * D, st));
       TRY(pgnn_internal_edge_table_bwd2(w.S, 9, w.gaggr, D, 0, N, (int)D, grads + o[L_ET1], D, grads + o[L_ET2], 6, st));
@@ -314,6 +382,10 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
     TRY(pgnn_aggregate_bwd(w.gaggr, D, N, D, w.rowptr_s, w.nbr_s, PGNN_AGG_SUM, nullptr, w.rowptr_t, w.gh, D, stream));
     gy = w.gh;
     ldgy = D;
+  }
+  if (sc) {  // the side stream's last wgrad (and its use of the split-K workspace) before the embedding GEMM and before returning
+    PGNN_CUDA(cudaEventRecord(sc->join, wst));
+    PGNN_CUDA(cudaStreamWaitEvent(st, sc->join, 0));
   }
   // embedding tables: [120 + 3, D] = onehot^T . gh as a split-K weight-gradient GEMM (the two tables are adjacent in the flat
   // layout); the vector-atomics kernel remains the fallback (FFMA precision, TMA unavailable)
