@@ -11,6 +11,10 @@
 // each followed by BatchNorm1d(D) and, except after the last layer, ReLU (chem/model.py:267-276).
 #include "common.cuh"
 
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st);
 int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, int in_relu,
@@ -20,6 +24,8 @@ int pgnn_internal_aggregate_fwd(const float* x, int64_t ldx, const float* in_sca
 int pgnn_internal_chem_onehot(const int64_t* x, int64_t n, int rows1, int rows2, float* onehot, int64_t ld, cudaStream_t st);
 int pgnn_tc_linear_bwd_w_ws(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st);
+int pgnn_tc_linear_bwd_w_ws2(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int64_t M, int64_t N, int64_t K, float* gw,
+                             float* gb, float* partials, int64_t partial_floats, cudaStream_t st, bool in_kernel_fold_ok);
 int64_t pgnn_tc_wgrad_workspace_floats(int64_t M, int64_t N, int64_t K);
 
 namespace {
@@ -86,7 +92,7 @@ Ws carve(void* base, int type, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.invstd = c.take<float>(L * D);
   w.gz = c.take<float>(N * D);
   w.ga = c.take<float>(N * D);
-  w.gxl = c.take<float>(N * HD);
+  w.gxl = c.take<float>(2 * N * HD);   // two copies by layer parity: the side-stream wgrad of layer l reads one while layer l-1 writes the other
   w.gh = c.take<float>(N * D);
   w.wpart_floats = pgnn_tc_wgrad_workspace_floats(N, HD, D);
   {
@@ -105,6 +111,40 @@ Ws carve(void* base, int type, int64_t N, int64_t E, int64_t L, int64_t D) {
   w.scratch = c.take<char>(sb);
   w.total = c.off;
   return w;
+}
+
+// weight-gradient GEMMs on a side stream, as in encoder.cu: they only feed the gradient buffer, so they run under the next
+// layer's BatchNorm / attention / gather kernels instead of in front of them.  PGNN_WGRAD_STREAM=0 disables.
+struct SideCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t gxl_ready[2] = {}, w_done[2] = {}, join = nullptr;
+  bool ok = false;
+};
+SideCtx* side_ctx(cudaStream_t main_stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SideCtx*> all;
+  static int enabled = -1;
+  std::lock_guard<std::mutex> g(mu);
+  if (enabled < 0) {
+    const char* e = getenv("PGNN_WGRAD_STREAM");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  auto key = std::make_pair(dev, main_stream);
+  auto it = all.find(key);
+  if (it != all.end()) return it->second->ok ? it->second : nullptr;
+  SideCtx* c = new SideCtx();
+  all[key] = c;
+  bool ok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&c->gxl_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->w_done[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  c->ok = ok;
+  return ok ? c : nullptr;
 }
 
 bool valid_type(int t) { return t == PGNN_CONV_GCN || t == PGNN_CONV_SAGE || t == PGNN_CONV_GAT; }
@@ -228,21 +268,26 @@ int pgnn_chem_conv_backward(int conv_type, const void* const* params, const floa
   Ws w = carve(workspace, conv_type, N, E, L, D);
   const float* gy = g_node_rep;
   int64_t ldgy = ldg;
+  SideCtx* sc = precision == 1 ? side_ctx(st) : nullptr;
+  cudaStream_t wst = sc ? sc->side : st;
   for (int64_t l = L - 1; l >= 0; --l) {
     const void* const* p = params + P_LAYER0 + l * PL;
     const int64_t* o = off + P_LAYER0 + l * PL;
     const bool last = l == L - 1;
+    const int par = (int)(l & 1);
     const float* xl = w.xl + l * N * HD;
     const float* z = w.z + l * N * D;
     const float* hin = l == 0 ? w.h0 : w.hout + (l - 1) * N * D;
+    float* gxl = w.gxl + (sc ? par * N * HD : 0);
     const float* gamma = (const float*)p[gat ? A_GAMMA : G_GAMMA];
     const float* beta = (const float*)p[gat ? A_BETA : G_BETA];
     TRY(pgnn_bn_bwd(gy, ldgy, z, D, N, D, gamma, beta, w.mean + l * D, w.invstd + l * D, !last, w.gz, D, grads + o[gat ? A_GAMMA : G_GAMMA],
                     grads + o[gat ? A_BETA : G_BETA], w.scratch, w.scratch_bytes, stream));
+    if (sc) PGNN_CUDA(cudaStreamWaitEvent(st, sc->w_done[par], 0));  // layer l+2's wgrad has finished reading this copy of gxl
     if (gat) {
       // gT [9, HD] lands on the two adjacent bond-table gradients
       TRY(pgnn_gat_bwd(w.gz, D, xl, N, kHeads, D, (const float*)p[A_ATT], w.T + l * 9 * HD, 0, edge_attr, w.rowptr_t, w.nbr_t, w.eid_t, w.rowptr_s,
-                       w.nbr_s, w.eid_s, E, kSlope, w.alpha + l * (E + N) * kHeads, w.pq + l * N * kHeads * 2, w.gxl, grads + o[A_ATT],
+                       w.nbr_s, w.eid_s, E, kSlope, w.alpha + l * (E + N) * kHeads, w.pq + l * N * kHeads * 2, gxl, grads + o[A_ATT],
                        grads + o[A_ET1], grads + o[A_BIAS], w.scratch, w.scratch_bytes, stream));
     } else {
       const float* ga = w.gz;
@@ -252,18 +297,34 @@ int pgnn_chem_conv_backward(int conv_type, const void* const* params, const floa
       }
       PGNN_CUDA(cudaMemsetAsync(grads + o[G_ET1], 0, sizeof(float) * 9 * D, st));
       TRY(pgnn_internal_edge_table_bwd2(w.S, 9, ga, D, 0, N, (int)D, grads + o[G_ET1], D, grads + o[G_ET2], 6, st));
-      TRY(pgnn_aggregate_bwd(ga, D, N, D, w.rowptr_s, w.nbr_s, agg_mode(conv_type), w.dinv, w.rowptr_t, w.gxl, D, stream));
+      TRY(pgnn_aggregate_bwd(ga, D, N, D, w.rowptr_s, w.nbr_s, agg_mode(conv_type), w.dinv, w.rowptr_t, gxl, D, stream));
     }
-    // Linear backward: weight + bias gradients (split-K partial tiles folded inside the GEMM), then the input gradient
+    // Linear backward: weight + bias gradients (side stream), then the input gradient
+    if (sc) {
+      PGNN_CUDA(cudaEventRecord(sc->gxl_ready[par], st));
+      PGNN_CUDA(cudaStreamWaitEvent(wst, sc->gxl_ready[par], 0));
+    }
     int rc = PGNN_EUNSUPPORTED;
     if (precision == 1)
-      rc = pgnn_tc_linear_bwd_w_ws(w.gxl, HD, hin, D, N, HD, D, grads + o[gat ? A_W : G_W], grads + o[gat ? A_B : G_B], w.wpart, w.wpart_floats, st);
-    if (rc == PGNN_EUNSUPPORTED)
-      rc = pgnn_linear_bwd_w(w.gxl, HD, hin, D, N, HD, D, grads + o[gat ? A_W : G_W], grads + o[gat ? A_B : G_B], precision, stream);
+      rc = pgnn_tc_linear_bwd_w_ws2(gxl, HD, hin, D, N, HD, D, grads + o[gat ? A_W : G_W], grads + o[gat ? A_B : G_B], w.wpart, w.wpart_floats, wst,
+                                    sc == nullptr);
+    if (rc == PGNN_EUNSUPPORTED) {
+      if (sc) {
+        PGNN_CUDA(cudaEventRecord(sc->join, wst));
+        PGNN_CUDA(cudaStreamWaitEvent(st, sc->join, 0));
+      }
+      rc = pgnn_linear_bwd_w(gxl, HD, hin, D, N, HD, D, grads + o[gat ? A_W : G_W], grads + o[gat ? A_B : G_B], precision, stream);
+    } else if (sc) {
+      PGNN_CUDA(cudaEventRecord(sc->w_done[par], wst));
+    }
     if (rc != PGNN_OK) return rc;
-    TRY(pgnn_linear_bwd_x(w.gxl, HD, (const float*)p[gat ? A_W : G_W], N, HD, D, nullptr, 0, w.gh, D, precision, stream));
+    TRY(pgnn_linear_bwd_x(gxl, HD, (const float*)p[gat ? A_W : G_W], N, HD, D, nullptr, 0, w.gh, D, precision, stream));
     gy = w.gh;
     ldgy = D;
+  }
+  if (sc) {  // the side stream's last wgrad (and its use of the split-K workspace) before the embedding GEMM and before returning
+    PGNN_CUDA(cudaEventRecord(sc->join, wst));
+    PGNN_CUDA(cudaStreamWaitEvent(st, sc->join, 0));
   }
   int rc_e = PGNN_EUNSUPPORTED;
   if (precision == 1)

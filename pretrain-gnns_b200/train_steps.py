@@ -116,6 +116,7 @@ class ContextPredStep(_Step):
         self.model_substruct = chem.GNN(NUM_LAYER, EMB, JK="last", drop_ratio=0, gnn_type="gin").to(device).train()
         self.model_context = chem.GNN(3, EMB, JK="last", drop_ratio=0, gnn_type="gin").to(device).train()
         self.modules = [self.model_substruct, self.model_context]
+        self.concurrent, self._side = True, None   # context encoder on a second CUDA stream (see scores)
         self.workload = "chem pretrain_contextpred 5-layer GIN emb_dim=300 batch_size=%d, substruct + 3-layer context encoder (BASELINE configs[2])" % batch_size
 
     KEYS = CONTEXT_KEYS
@@ -131,10 +132,25 @@ class ContextPredStep(_Step):
 
     def scores(self, b):
         B = b["center_substruct_idx"].shape[0]
+        # The two encoders are independent until the dot products (the script runs them back to back, :54-57), and at
+        # B = 128 neither fills the chip (17 and 10 row tiles of 128 nodes): the context encoder runs on a second stream,
+        # forward and — autograd replays a node's backward on its forward stream — backward alike.
+        main = torch.cuda.current_stream() if b["x_context"].is_cuda else None
+        if main is not None and self.concurrent:
+            if self._side is None:
+                self._side = torch.cuda.Stream(b["x_context"].device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                ov = ops.row_gather(self.model_context(b["x_context"], b["edge_index_context"], b["edge_attr_context"]),
+                                    b["overlap_context_substruct_idx"])
+            ov.record_stream(main)
+        else:
+            ov = ops.row_gather(self.model_context(b["x_context"], b["edge_index_context"], b["edge_attr_context"]),
+                                b["overlap_context_substruct_idx"])
         sub = ops.row_gather(self.model_substruct(b["x_substruct"], b["edge_index_substruct"], b["edge_attr_substruct"]),
                              b["center_substruct_idx"])
-        ov = ops.row_gather(self.model_context(b["x_context"], b["edge_index_context"], b["edge_attr_context"]),
-                            b["overlap_context_substruct_idx"])
+        if main is not None and self.concurrent:
+            main.wait_stream(self._side)
         ctx = ops.global_mean_pool(ov, b["batch_overlapped_context"], B)   # one segment per graph of the batch
         pos = ops.shifted_rowdot(sub, ctx, 0)
         neg = torch.cat([ops.shifted_rowdot(sub, ctx, i + 1) for i in range(self.neg_samples)], dim=0)
