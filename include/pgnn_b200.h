@@ -276,6 +276,9 @@ PGNN_API int pgnn_bce_logits_fwd(const float* logits, int64_t ld, int64_t M, int
 PGNN_API int64_t pgnn_chem_gin_num_params(int64_t L);
 PGNN_API int pgnn_chem_gin_grad_offsets(int64_t L, int64_t D, int64_t* offsets);
 PGNN_API int64_t pgnn_chem_gin_workspace_bytes(int64_t N, int64_t E, int64_t L, int64_t D);
+/* test aid: byte offsets in the workspace of z1 [L][N][2D] (post-ReLU hidden), z2 [L][N][D] (pre-BatchNorm), BatchNorm batch mean
+ * [L][D] and invstd [L][D] after a training forward: lets a test recover the ReLU decisions the encoder took */
+PGNN_API int pgnn_chem_gin_debug_layout(int64_t N, int64_t E, int64_t L, int64_t D, int64_t* out4);
 PGNN_API int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mean, void* const* bn_running_var,
                                    void* const* bn_num_batches_tracked, const int64_t* x, const int64_t* edge_index,
                                    const int64_t* edge_attr, int64_t N, int64_t E, int64_t L, int64_t D, int training,

@@ -80,6 +80,9 @@ LOSSES = {"masking": masking_loss, "contextpred": contextpred_loss, "bio_supervi
           "graphsage": lambda L, b: masking_loss(L, b, "graphsage")}
 
 
+LAST_RELU_TRACE = None   # the fp64 run's ReLU pre-activations of the most recent grads_fp32_fp64 call (tests compare decisions)
+
+
 def grads_fp32_fp64(loss_fn, P, b):
     """Differentiate `loss_fn` on fp32 and fp64 leaf copies of P.  -> (loss32, aux32, grads32, loss64, aux64, grads64, near_zero):
     near_zero = number of ReLU pre-activations of the fp64 run within rounding distance of the kink (gnn_oracle)."""
@@ -91,7 +94,9 @@ def grads_fp32_fp64(loss_fn, P, b):
         try:
             loss, aux = loss_fn(L, b)
             if dt == torch.float64:
+                global LAST_RELU_TRACE
                 near = O.near_zero_preactivations(O.RELU_TRACE)
+                LAST_RELU_TRACE = O.RELU_TRACE
         finally:
             O.RELU_TRACE = None
         loss.backward()

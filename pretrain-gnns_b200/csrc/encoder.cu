@@ -194,6 +194,20 @@ int64_t pgnn_chem_gin_workspace_bytes(int64_t N, int64_t E, int64_t L, int64_t D
   return carve(nullptr, N, E, L, D).total;
 }
 
+// Development / test aid: byte offsets inside the workspace of the saved activations a test needs to reconstruct the
+// ReLU decisions the encoder actually took: out[0] = z1 (post-ReLU hidden activations, [L][N][2D]), out[1] = z2 (pre-BatchNorm
+// layer outputs, [L][N][D]), out[2] = BatchNorm batch mean [L][D], out[3] = invstd [L][D].
+int pgnn_chem_gin_debug_layout(int64_t N, int64_t E, int64_t L, int64_t D, int64_t* out4) {
+  PGNN_CHECK_ARG(N >= 0 && E >= 0 && L >= 1 && D > 0 && out4);
+  char* base = reinterpret_cast<char*>(0x1000);  // carve() only does pointer arithmetic
+  Ws w = carve(base, N, E, L, D);
+  out4[0] = reinterpret_cast<char*>(w.z1) - base;
+  out4[1] = reinterpret_cast<char*>(w.z2) - base;
+  out4[2] = reinterpret_cast<char*>(w.mean) - base;
+  out4[3] = reinterpret_cast<char*>(w.invstd) - base;
+  return PGNN_OK;
+}
+
 int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mean, void* const* bn_running_var,
                           void* const* bn_num_batches_tracked, const int64_t* x, const int64_t* edge_index,
                           const int64_t* edge_attr, int64_t N, int64_t E, int64_t L, int64_t D, int training, float momentum, float eps,

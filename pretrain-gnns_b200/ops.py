@@ -675,6 +675,8 @@ class ChemGinPlan:
         # would overwrite the buffer whose views the engine still holds as the first node's gradients.  (A forward whose
         # graph is dropped without a backward leaves the count raised: the fresh-buffer path is then taken, which is safe.)
         self.live_forwards = 0
+        self.keep_workspace = False   # tests: keep the last training forward's workspace (relu_masks)
+        self.last_ws = None
 
 
 class _ChemGinEncoder(Function):
@@ -708,6 +710,8 @@ class _ChemGinEncoder(Function):
                                         float(bns[0].eps), _precision, _p(out), D, _p(ws), wsb, _st()), "chem_gin_forward")
         ctx.plan, ctx.ws, ctx.wsb, ctx.ptrs, ctx.x, ctx.dims, ctx.training = plan, ws, wsb, ptrs, x, (N, E, L, D), training
         ctx.keep = params  # the pointer table refers to these storages
+        if training and plan.keep_workspace:
+            plan.last_ws = (ws, (N, E, L, D))
         if training and any(ctx.needs_input_grad[5:]):
             plan.live_forwards += 1
         if _VALIDATE:
@@ -732,6 +736,26 @@ class _ChemGinEncoder(Function):
         plan.last_flat_grad = flat
         grads = [v if len(s) == 1 else v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)]
         return (None, None, None, None, None) + tuple(gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[5:]))
+
+
+def chem_gin_relu_masks(plan: ChemGinPlan, gnn):
+    """The ReLU decisions of the last training forward of the fused GIN encoder (plan.keep_workspace = True), in the order the
+    reference takes them: per layer the MLP's hidden units [N, 2D], then (all but the last layer) the post-BatchNorm units [N, D]."""
+    ws, (N, E, L, D) = plan.last_ws
+    off = (_ct.c_int64 * 4)()
+    check(lib.pgnn_chem_gin_debug_layout(N, E, L, D, off), "chem_gin_debug_layout")
+    f = lambda o, n: ws[o:o + 4 * n].view(torch.float32)
+    z1 = f(off[0], L * N * 2 * D).view(L, N, 2 * D)
+    z2 = f(off[1], L * N * D).view(L, N, D)
+    mean, invstd = f(off[2], L * D).view(L, D), f(off[3], L * D).view(L, D)
+    masks = []
+    for l in range(L):
+        masks.append(z1[l] > 0)
+        if l != L - 1:
+            bn = gnn.batch_norms[l]
+            xhat = (z2[l] - mean[l]) * invstd[l]
+            masks.append(torch.addcmul(bn.bias.detach(), xhat, bn.weight.detach()) > 0)   # the backward's own test: fma(xhat, gamma, beta) > 0
+    return masks
 
 
 def chem_gin_encoder(plan: ChemGinPlan, x, edge_index, edge_attr, training: bool):

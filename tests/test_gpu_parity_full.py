@@ -28,9 +28,23 @@ def _compare(name, step, config, b, P, aux_fn, loss_fn=None):
     loss_fn = loss_fn or S.LOSSES[config]
     torch.set_num_threads(min(16, torch.get_num_threads()))
     l32, a32, g32, l64, a64, g64, near = S.grads_fp32_fp64(loss_fn, P, b)
+    trace64 = S.LAST_RELU_TRACE
     step.load_state(P)
     d = _dev(b)
+    plan = getattr(getattr(step, "model", None), "_fused_plan", lambda: None)()
+    track = plan is not None and hasattr(plan, "keep_workspace") and config == "masking"
+    if track:
+        plan.keep_workspace = True
     loss = step(d)
+    flips = None
+    if track:
+        # ReLU decisions the fused GIN encoder actually took vs the fp64 oracle's: the allowance below needs a REAL flip
+        ops = importlib.import_module("pretrain-gnns_b200.ops")
+        mine = ops.chem_gin_relu_masks(plan, step.model)
+        assert len(mine) == len(trace64)
+        flips = int(sum(int((m.cpu() != (t > 0)).sum()) for m, t in zip(mine, trace64)))
+        plan.keep_workspace, plan.last_ws = False, None
+        near = min(near, flips)   # no flip, no allowance
     grads = [(k, p.grad) for k, p in step.named_parameters()]
     assert all(g is not None for _, g in grads)
     with torch.no_grad():
@@ -44,7 +58,7 @@ def _compare(name, step, config, b, P, aux_fn, loss_fn=None):
     rows.append(dict(kind="loss", name="loss", err=lerr, err_ref32=lref, ok=lerr <= max(2e-6, 3 * lref)))
     ok &= rows[-1]["ok"]
     ok &= gradient_check(grads, g32, g64, near, rows)
-    write_report(name, rows, dict(near_zero_preactivations=near, loss=float(loss), loss_oracle64=float(l64)))
+    write_report(name, rows, dict(near_zero_preactivations=near, relu_flips_detected=flips, loss=float(loss), loss_oracle64=float(l64)))
     bad = [r for r in rows if not r["ok"]]
     assert ok, bad[:8]
 
