@@ -182,14 +182,15 @@ k_aggregate_bwd(const float* __restrict__ g, int64_t ldg, int64_t n, int C4, con
   }
 }
 
-// gT[q][c] = sum_i S[i][q] * g[i][g_off + c].  Blocks of 32 columns x 8 row-lanes sweep 256 rows with
+// gT[q][c] = sum_i S[i][q] * g[i][g_off + c].  Blocks of 32 columns x 8 row-lanes sweep 64 rows (8 per thread: the
+// per-thread row loop is a chain of dependent-latency loads, 32 rows per thread made the kernel 17 us at N = 6 k) with
 // coalesced 128-byte loads; each thread keeps Q register accumulators (S rows are warp-broadcast loads), the 8
 // row-lanes are folded in shared memory and one fp32 atomicAdd per (block, q, c) folds the row chunks.
-constexpr int kTblRows = 256;
+constexpr int kTblRowsSmall = 64, kTblRowsLarge = 256;  // rows per block: small batches are latency-bound, large ones atomics-bound
 constexpr int kMaxQ = 16;
 __global__ void __launch_bounds__(256)
 k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g, int64_t ldg, int64_t g_off, int64_t n,
-                 int C, float* __restrict__ gT, int64_t ldt, float* __restrict__ gT2, int q_split) {
+                 int C, float* __restrict__ gT, int64_t ldt, float* __restrict__ gT2, int q_split, int kTblRows) {
   pdl_prologue();
   __shared__ float red[8][kMaxQ][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -200,7 +201,7 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
 #pragma unroll
   for (int q = 0; q < kMaxQ; ++q) acc[q] = 0.f;
   if (c < C) {
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t r = r0 + w; r < r1; r += 8) {
       const float v = g[r * ldg + g_off + c];
       const float* s = S + r * Q;
@@ -324,8 +325,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st) {
   if (n == 0) return PGNN_OK;
-  dim3 grid((unsigned)ceil_div(n, kTblRows), (unsigned)ceil_div(C, 32));
-  PGNN_CUDA(pgnn_launch(k_edge_table_bwd, dim3(grid), dim3(256), 0, st, S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split));
+  const int rows = n >= 16384 ? kTblRowsLarge : kTblRowsSmall;
+  dim3 grid((unsigned)ceil_div(n, rows), (unsigned)ceil_div(C, 32));
+  PGNN_CUDA(pgnn_launch(k_edge_table_bwd, dim3(grid), dim3(256), 0, st, S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split, rows));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
 }
