@@ -601,7 +601,7 @@ int pgnn_tc_linear_bwd_w_ws2(const float* gy, int64_t ldgy, const float* x, int6
   if (rc != PGNN_OK) return rc;
   if (gb) {
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
-    const int rows_per = 256;
+    const int rows_per = M >= 16384 ? 256 : 64;  // 8 rows per thread for small batches: the row loop is a latency chain
     dim3 g2((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, rows_per));
     PGNN_CUDA(pgnn_launch(k_colsum_tc, dim3(g2), dim3(256), 0, st, gy, ldgy, (int)M, (int)N, rows_per, gb));
     PGNN_LAUNCH_CHECK();

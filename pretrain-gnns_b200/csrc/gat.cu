@@ -458,8 +458,8 @@ int pgnn_gat_bwd(const float* g, int64_t ldg, const float* xl, int64_t num_nodes
   PGNN_CUDA(pgnn_launch(k_gat_bwd_rterm, dim3((unsigned)ceil_div(H * D, 128)), dim3(128), 0, st, w.Bsum, att, T, Q, (int)H, (int)D, gatt, gT));
   PGNN_LAUNCH_CHECK();
   {
-    int64_t splits = ceil_div(num_nodes, 256);
-    if (splits > 64) splits = 64;
+    int64_t splits = ceil_div(num_nodes, 32);   // ~32 rows per thread (a serial, latency-bound loop): more, shorter row chunks
+    if (splits > 512) splits = 512;
     const int rows_per = (int)ceil_div(num_nodes, splits);
     dim3 grid((unsigned)ceil_div(D, 128), (unsigned)ceil_div(num_nodes, rows_per));
     PGNN_CUDA(pgnn_launch(k_colsum_atomic, dim3(grid), dim3(128), 0, st, g, ldg, num_nodes, (int)D, rows_per, gbias));
