@@ -12,6 +12,8 @@ and the same parameter / buffer names, so every shipped `.pth` loads with all ke
 is underneath: no torch_geometric, no per-edge tensors.  Each batch is bucketed once (ops.Graph), the bond
 embedding sum is folded into a per-node 9-bin summary, and every op is a CUDA kernel behind the C ABI.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -156,6 +158,8 @@ class GNN(nn.Module):
         """The whole-encoder kernels (pgnn_chem_gin_* / pgnn_chem_conv_*) cover every gnn_type with JK='last', the conv's
         default aggregation (and GAT's 2 heads / slope 0.2) and no live dropout."""
         if not (self.fused and self.JK == "last" and (self.drop_ratio == 0 or not self.training)):
+            return None
+        if self._gnn_type != "gin" and os.environ.get("PGNN_FUSED_CONV", "1") == "0":   # development switch
             return None
         if any(conv.aggr != self._DEFAULT_AGGR[self._gnn_type] for conv in self.gnns) or any(bn.training != self.training for bn in self.batch_norms):
             return None

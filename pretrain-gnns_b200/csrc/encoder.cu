@@ -158,6 +158,16 @@ SideCtx* side_ctx(cudaStream_t main_stream) {
   return ok ? c : nullptr;
 }
 
+// PGNN_EMBED_GEMM=0: embedding-table gradient through the vector-atomics kernel instead of the one-hot GEMM (development switch)
+inline bool embed_gemm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_EMBED_GEMM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 #define TRY(call)                 \
   do {                            \
     int rc__ = (call);            \
@@ -404,7 +414,7 @@ int pgnn_chem_gin_backward(const void* const* params, const float* g_node_rep, i
   // embedding tables: [120 + 3, D] = onehot^T . gh as a split-K weight-gradient GEMM (the two tables are adjacent in the flat
   // layout); the vector-atomics kernel remains the fallback (FFMA precision, TMA unavailable)
   int rc_e = PGNN_EUNSUPPORTED;
-  if (precision == 1 && off[P_XEMB2] == off[P_XEMB1] + (int64_t)kAtomRows * D)
+  if (precision == 1 && embed_gemm_enabled() && off[P_XEMB2] == off[P_XEMB1] + (int64_t)kAtomRows * D)
     rc_e = pgnn_tc_linear_bwd_w_ws(w.onehot, kOneHotLd, w.gh, D, N, kAtomRows + kChiralRows, D, grads + off[P_XEMB1], nullptr, w.wpart,
                                    w.wpart_floats, st);
   if (rc_e == PGNN_EUNSUPPORTED)

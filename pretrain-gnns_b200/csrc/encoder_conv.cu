@@ -149,6 +149,16 @@ SideCtx* side_ctx(cudaStream_t main_stream) {
 
 bool valid_type(int t) { return t == PGNN_CONV_GCN || t == PGNN_CONV_SAGE || t == PGNN_CONV_GAT; }
 
+// PGNN_EMBED_GEMM=0: embedding-table gradient through the vector-atomics kernel instead of the one-hot GEMM (development switch)
+inline bool embed_gemm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_EMBED_GEMM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 #define TRY(call)                     \
   do {                                \
     int rc__ = (call);                \
@@ -327,7 +337,7 @@ int pgnn_chem_conv_backward(int conv_type, const void* const* params, const floa
     PGNN_CUDA(cudaStreamWaitEvent(st, sc->join, 0));
   }
   int rc_e = PGNN_EUNSUPPORTED;
-  if (precision == 1)
+  if (precision == 1 && embed_gemm_enabled())
     rc_e = pgnn_tc_linear_bwd_w_ws(w.onehot, kOneHotLd, w.gh, D, N, kAtomRows + kChiralRows, D, grads + off[P_XEMB1], nullptr, w.wpart, w.wpart_floats, st);
   if (rc_e == PGNN_EUNSUPPORTED)
     rc_e = pgnn_chem_embed_bwd(x, w.gh, D, N, D, grads + off[P_XEMB1], kAtomRows, grads + off[P_XEMB2], kChiralRows, stream);

@@ -8,7 +8,19 @@
 // accumulation makes E[x^2]-E[x]^2 safe (relative error ~1e-16 * mean^2/var).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
+
+// PGNN_BN_V4=0 falls back to the scalar sweeps (development switch)
+inline bool bn_v4_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_BN_V4");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 constexpr int kStatRows = 128;  // rows per block of the statistics sweeps
 
@@ -458,7 +470,7 @@ int pgnn_internal_bn_bwd_colsum(const float* gy, int64_t ldgy, const float* x, i
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   PGNN_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * C, st));
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (C % 4 == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && ldgx % 4 == 0 && a16(gy) && a16(x) && a16(gx) && a16(gamma) && a16(beta) &&
+  if (bn_v4_enabled() && C % 4 == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && ldgx % 4 == 0 && a16(gy) && a16(x) && a16(gx) && a16(gamma) && a16(beta) &&
       a16(save_mean) && a16(save_invstd)) {
     dim3 gv((unsigned)ceil_div(C, 128), (unsigned)ceil_div(M, kVecRows));
     PGNN_CUDA(pgnn_launch(k_bn_bwd_stats_v4, dim3(gv), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
@@ -495,7 +507,7 @@ int pgnn_bn_fwd_train(const float* x, int64_t ldx, int64_t M, int64_t C, const f
   double* acc = reinterpret_cast<double*>(workspace);
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const bool v4 = C % 4 == 0 && ldx % 4 == 0 && a16(x) && a16(gamma) && a16(beta) && a16(save_mean) && a16(save_invstd) &&
+  const bool v4 = bn_v4_enabled() && C % 4 == 0 && ldx % 4 == 0 && a16(x) && a16(gamma) && a16(beta) && a16(save_mean) && a16(save_invstd) &&
                   (!y || (ldy % 4 == 0 && a16(y)));
   if (v4) {
     dim3 gv((unsigned)ceil_div(C, 128), (unsigned)ceil_div(M, kVecRows));
@@ -541,7 +553,7 @@ int pgnn_bn_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, int6
   PGNN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   {
     auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    if (C % 4 == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && ldgx % 4 == 0 && a16(gy) && a16(x) && a16(gx) && a16(gamma) && a16(beta) &&
+    if (bn_v4_enabled() && C % 4 == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && ldgx % 4 == 0 && a16(gy) && a16(x) && a16(gx) && a16(gamma) && a16(beta) &&
         a16(save_mean) && a16(save_invstd)) {
       dim3 gv((unsigned)ceil_div(C, 128), (unsigned)ceil_div(M, kVecRows));
       PGNN_CUDA(pgnn_launch(k_bn_bwd_stats_v4, dim3(gv), dim3(256), 0, st, gy, ldgy, x, ldx, (int)M, (int)C, gamma, beta, save_mean, save_invstd, relu, acc));
