@@ -34,7 +34,7 @@ __device__ __forceinline__ bool bucket_key_ok(const BucketSet& B, int64_t i, int
   return ok;
 }
 
-__global__ void k_histogram(BucketPair P, int64_t stride, int64_t val_stride, int64_t n, int64_t num_buckets, unsigned int* __restrict__ err) {
+__global__ void k_histogram(const __grid_constant__ BucketPair P, int64_t stride, int64_t val_stride, int64_t n, int64_t num_buckets, unsigned int* __restrict__ err) {
   pdl_prologue();
   const BucketSet& B = P.s[blockIdx.y];
   bool bad = false;
@@ -50,7 +50,7 @@ __global__ void k_histogram(BucketPair P, int64_t stride, int64_t val_stride, in
 // One CTA of 1024 threads per key set.  Each thread owns a CONTIGUOUS run of ceil(n / 1024) elements: it sums its run, the CTA
 // scans the 1024 run totals once (two shuffle scans + one barrier pair), and the thread rewrites its run — one pass with a
 // single block-wide synchronisation instead of one per 1024-element tile (node counts are 6 k - 32 k here: 6 - 32 tiles).
-__global__ void __launch_bounds__(1024) k_exclusive_scan(BucketPair P, int64_t n) {
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const __grid_constant__ BucketPair P, int64_t n) {
   pdl_prologue();
   int* counts = P.s[blockIdx.x].counts;
   int* rowptr = P.s[blockIdx.x].rowptr;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(BucketPair P, int64_t n
   if (threadIdx.x == 1023) rowptr[n] = warp_tot[31];
 }
 
-__global__ void k_place(BucketPair P, int64_t stride, int64_t val_stride, int64_t n, int64_t num_buckets) {
+__global__ void k_place(const __grid_constant__ BucketPair P, int64_t stride, int64_t val_stride, int64_t n, int64_t num_buckets) {
   pdl_prologue();
   const BucketSet& B = P.s[blockIdx.y];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -102,7 +102,7 @@ __global__ void k_place(BucketPair P, int64_t stride, int64_t val_stride, int64_
 // The atomic placement leaves every bucket holding the right SET in arbitrary order; rank each element
 // among its bucket-mates by original position to obtain the stable order (rank by counting: bucket sizes
 // are in-degrees / graph sizes / vocabulary hits, so the quadratic term stays tiny).
-__global__ void k_rank_in_bucket(BucketPair P, int64_t stride, int64_t val_stride, int64_t num_buckets) {
+__global__ void k_rank_in_bucket(const __grid_constant__ BucketPair P, int64_t stride, int64_t val_stride, int64_t num_buckets) {
   pdl_prologue();
   const BucketSet& B = P.s[blockIdx.y];
   const int64_t placed = B.rowptr[num_buckets];  // == n unless out-of-range keys were dropped
