@@ -68,15 +68,25 @@ struct PgnnBnFold {
   float* save_invstd = nullptr;
   float momentum = 0.1f, eps = 1e-5f;
   int M = 0;
+  double inv_m = 0.0, unbias = 1.0;  // 1 / M and M / (M - 1), formed on the host (set_rows)
+  void set_rows(int rows) {
+    M = rows;
+    inv_m = rows > 0 ? 1.0 / (double)rows : 0.0;
+    unbias = rows > 1 ? (double)rows / (double)(rows - 1) : 1.0;
+  }
 };
 
 // per-column BatchNorm constants from the accumulated sums; `leader` performs the running-statistics side effects
+// Every CTA of the consumer runs this for its columns, so it must be cheap: the fp64 part is two multiplies and one FMA (the
+// sums are fp64 because E[x^2] - E[x]^2 cancels); the reciprocal square root is taken in fp32 like torch's own BatchNorm
+// kernels do.  (With fp64 division and square root — software sequences of ~100 instructions each — this prologue was most
+// of the 450 instructions per thread ncu counted in k_aggregate_fwd: profiles/r02_kernels_masking.md.)
 __device__ __forceinline__ void bn_fold_column(const PgnnBnFold& f, int C, int c, bool leader, float& scale, float& shift) {
   const double s = f.acc[c], ss = f.acc[(int64_t)C + c];
-  const double mean = s / f.M;
-  double var = ss / f.M - mean * mean;
+  const double mean = s * f.inv_m;
+  double var = fma(ss, f.inv_m, -mean * mean);
   var = var < 0.0 ? 0.0 : var;
-  const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+  const float invstd = 1.0f / sqrtf((float)var + f.eps);
   const float meanf = (float)mean;
   scale = f.gamma[c] * invstd;
   shift = fmaf(-meanf, scale, f.beta[c]);
@@ -85,8 +95,7 @@ __device__ __forceinline__ void bn_fold_column(const PgnnBnFold& f, int C, int c
     if (f.save_invstd) f.save_invstd[c] = invstd;
     if (f.running_mean) f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * meanf;
     if (f.running_var) {
-      const double unbiased = var * ((double)f.M / (double)(f.M > 1 ? f.M - 1 : 1));
-      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(var * f.unbias);
     }
     if (c == 0 && f.nbt) *f.nbt += 1;
   }

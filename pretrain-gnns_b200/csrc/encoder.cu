@@ -138,7 +138,8 @@ SideCtx* side_ctx(cudaStream_t main_stream) {
     const char* e = getenv("PGNN_WGRAD_STREAM");
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!enabled) return nullptr;
+  // the per-kernel timing mode (pgnn_profile_enable) wants each kernel's own duration: no concurrent stream while it is on
+  if (!enabled || g_pgnn_profile_on.load(std::memory_order_relaxed) != 0) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   auto key = std::make_pair(dev, main_stream);
@@ -268,7 +269,7 @@ int pgnn_chem_gin_forward(const void* const* params, void* const* bn_running_mea
       fold.running_mean = (float*)bn_running_mean[l]; fold.running_var = (float*)bn_running_var[l];
       fold.nbt = bn_num_batches_tracked ? (int64_t*)bn_num_batches_tracked[l] : nullptr;
       fold.save_mean = w.mean + l * D; fold.save_invstd = w.invstd + l * D;
-      fold.momentum = momentum; fold.eps = eps; fold.M = (int)N;
+      fold.momentum = momentum; fold.eps = eps; fold.set_rows((int)N);
       if (last) {
         TRY(pgnn_internal_bn_apply_fold(z2, D, N, D, fold, 0, node_rep, ld_out, as_stream(stream)));
       } else {

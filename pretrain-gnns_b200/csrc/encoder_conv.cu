@@ -129,7 +129,8 @@ SideCtx* side_ctx(cudaStream_t main_stream) {
     const char* e = getenv("PGNN_WGRAD_STREAM");
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!enabled) return nullptr;
+  // the per-kernel timing mode (pgnn_profile_enable) wants each kernel's own duration: no concurrent stream while it is on
+  if (!enabled || g_pgnn_profile_on.load(std::memory_order_relaxed) != 0) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   auto key = std::make_pair(dev, main_stream);

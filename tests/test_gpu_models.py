@@ -106,7 +106,9 @@ def test_fused_and_layerwise_conv_paths_agree(t):
     gmax = max(float(g.abs().max()) for g in res[1][1].values())
     for k, g in res[1][1].items():
         scale = max(float(g.abs().max()), 1e-3 * gmax)
-        assert float((res[0][1][k] - g).abs().max()) <= 2e-4 * scale, k
+        # + an absolute term on the model's gradient scale: a bias in front of BatchNorm has a structurally zero gradient,
+        # i.e. pure rounding noise (~1e-6 of the largest gradient) on both paths
+        assert float((res[0][1][k] - g).abs().max()) <= 2e-4 * scale + 3e-6 * gmax, k
     for k in res[0][2]:
         assert torch.allclose(res[0][2][k].float(), res[1][2][k].float(), atol=1e-5, rtol=1e-5), k
     with torch.no_grad():

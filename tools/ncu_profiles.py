@@ -60,12 +60,13 @@ def launches(args):
     print("wrote", args.dst)
 
 
-METRICS = {"gpu__time_duration.sum": "dur", "dram__bytes_read.sum": "dr", "dram__bytes_write.sum": "dw", "lts__t_bytes.sum": "l2",
+METRICS = {"gpu__time_duration.sum": "dur", "dram__bytes_read.sum": "dr", "dram__bytes_write.sum": "dw", "lts__t_sectors.sum": "l2",
+           "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor",
            "sm__warps_active.avg.pct_of_peak_sustained_active": "warps", "launch__registers_per_thread": "regs",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
            "lts__t_sectors_srcunit_tex_op_read.sum": "l2_rd_sectors", "smsp__inst_executed.sum": "inst"}
-SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3}
+SCALE = {"sector": 32, "byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3}
 
 
 def full(args):
@@ -81,13 +82,14 @@ def full(args):
             if m in col and r[col[m]] not in ("", "n/a"):
                 d[key].append(float(r[col[m]].replace(",", "")) * SCALE.get(units[col[m]], 1))
     out = ["# %s" % args.title, "", args.note, "",
-           "| kernel | launches | µs | DRAM read MB | DRAM write MB | L2 (lts) MB | tensor pipe % | warps active % | regs |",
-           "|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
+           "| kernel | launches | µs | DRAM read MB | DRAM write MB | L2 sectors MB | L2 throughput % | tensor pipe % | issue active % | warps active % | regs |",
+           "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     avg = lambda xs: sum(xs) / len(xs) if xs else float("nan")
     traffic = {}
     for k, d in per.items():
-        out.append("| `%s` | %d | %.2f | %.2f | %.2f | %.2f | %.1f | %.1f | %d |"
-                   % (k, len(d["dur"]), avg(d["dur"]), avg(d["dr"]) / 1e6, avg(d["dw"]) / 1e6, avg(d["l2"]) / 1e6, avg(d["tensor"]), avg(d["warps"]),
+        out.append("| `%s` | %d | %.2f | %.2f | %.2f | %.2f | %.1f | %.1f | %.1f | %.1f | %d |"
+                   % (k, len(d["dur"]), avg(d["dur"]), avg(d["dr"]) / 1e6, avg(d["dw"]) / 1e6, avg(d["l2"]) / 1e6, avg(d["l2_pct"]), avg(d["tensor"]),
+                      avg(d["issue"]), avg(d["warps"]),
                       int(avg(d["regs"])) if d["regs"] else -1))
         role = "gemm" if "k_gemm_3xtf32_tma" in k and args.gemm_pattern in k else ("gather" if k.startswith(args.gather_kernel) else None)
         if role and role not in traffic:
