@@ -363,7 +363,9 @@ def run_b200(args, rank, world, local_rank):
         gc.disable()  # a collection in the middle of the loop stalls the launch thread for milliseconds (seen as 2-9 ms steps)
         t0 = time.perf_counter()
         ticket, acc = None, 0.0
+        host_t = []
         for i in range(args.steps):
+            host_t.append(time.perf_counter())
             flush.zero_()  # L2 flush, outside the per-step event pair
             ev[i][0].record()
             if e2e:
@@ -391,6 +393,8 @@ def run_b200(args, rank, world, local_rank):
         gc.enable()
         launches = cabi.lib.pgnn_kernel_launch_count() - n0
         per = [a.elapsed_time(b) for a, b in ev]
+        host_t.append(t0 + wall)
+        timed.host_issue_ms = [1e3 * (b - a) for a, b in zip(host_t[:-1], host_t[1:])]  # host time per loop iteration (diagnostic)
         t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -398,7 +402,9 @@ def run_b200(args, rank, world, local_rank):
 
     with ClockSampler(local_rank) as clocks:
         ms_dev, launches, wall_dev, per_dev, _ = timed(False)
+        host_dev = timed.host_issue_ms
         ms_e2e, _, wall_e2e, per_e2e, mean_loss = timed(True)
+        host_e2e = timed.host_issue_ms
     graphs = B * world * args.steps
     wm = work_model(config, host[0])
 
@@ -427,7 +433,9 @@ def run_b200(args, rank, world, local_rank):
                                                             "--precision fp32 runs the exact FFMA kernels)" if ops.get_precision() != "fp32" else ""),
                    "grad_allreduce": (reducer.backend if reducer is not None else "none (1 GPU)"),
                    "per_step_ms": dist_stats(per_dev), "per_step_ms_e2e": dist_stats(per_e2e),
-                   "slowest_e2e_steps": sorted(((round(t, 3), i) for i, t in enumerate(per_e2e)), reverse=True)[:4],
+                   "slowest_steps": [(round(t, 3), i, round(host_dev[i], 3)) for t, i in sorted(((t, i) for i, t in enumerate(per_dev)), reverse=True)[:4]],
+                   "slowest_e2e_steps": [(round(t, 3), i, round(host_e2e[i], 3)) for t, i in sorted(((t, i) for i, t in enumerate(per_e2e)), reverse=True)[:4]],
+                   "slowest_steps_fields": "[device ms, step index, host ms spent issuing that loop iteration]",
                    "wall_ms_per_step_incl_flush": 1e3 * wall_dev / args.steps, "wall_ms_per_step_incl_flush_e2e": 1e3 * wall_e2e / args.steps,
                    "mean_loss_e2e": mean_loss, "gemm_flops_per_step": wm["gemm_flops_per_step"]},
         "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

@@ -386,6 +386,16 @@ PGNN_API int pgnn_adam_step(const PgnnAdamChunk* chunks, int64_t num_chunks, dou
 PGNN_API int64_t pgnn_allreduce_p2p_scratch_floats(int64_t n, int world);
 PGNN_API int pgnn_allreduce_p2p(void* const* bufs, void* const* flags, int rank, int world, int64_t n, float scale,
                                 float* scratch, int64_t scratch_floats, int64_t epoch, void* stream);
+/* One-kernel, OUT-OF-PLACE form (round 2): one launch, two flag exchanges instead of five launches and three barriers.
+ *   in / out : DEVICE arrays of `world` peer-mapped pointers to every rank's input / output buffer (n floats each, distinct
+ *              symmetric allocations); on return (stream order) out[rank] holds scale * sum over ranks of in[.], bit-identical
+ *              on every rank (fixed summation order); the input buffers are left untouched and may be rewritten
+ *   flags    : as above, but uint32[128] per rank: this entry uses words [64, 128)
+ *   mc_in / mc_out : multicast mappings of the buffers (both non-null: multimem.ld_reduce / multimem.st, the NVSwitch sums and
+ *              broadcasts; n % (4*world) == 0), else null
+ *   counter  : LOCAL device uint32, zero before the first call */
+PGNN_API int pgnn_allreduce_fused(void* const* in, void* const* out, void* const* flags, float* mc_in, float* mc_out,
+                                  unsigned int* counter, int rank, int world, int64_t n, float scale, int64_t epoch, void* stream);
 /* EXPERIMENTAL, not yet measured on hardware and not used by default: the same exchange with the NVSwitch doing the sum
  * (multimem.ld_reduce / multimem.st on the multicast mapping `mc_buf` of the symmetric buffer).  n % (4*world) == 0;
  * two flag barriers per call (own epoch counter; do not share a flag array with pgnn_allreduce_p2p). */

@@ -168,9 +168,163 @@ __device__ __forceinline__ void splitk_fold_in_kernel(const float* __restrict__ 
   }
 }
 
+// ---- TMA-store epilogue -------------------------------------------------------------------------------------------------
+// The tile leaves through the copy engine instead of through 256 threads' st.global: each warp turns its TMEM rows into FINAL
+// values (both accumulators summed, bias / ReLU / ReLU-mask applied in registers) and writes them into a [128 rows x 16 cols]
+// box in the SWIZZLE_64B layout (the 16-byte chunk index XORed with bits 1-2 of the row: the 8 lanes of a store phase hit 8
+// distinct bank groups); the four warps of a column half meet on a named barrier and one thread issues
+// cp.async.bulk.tensor (shared -> global) for the box while the next 16 columns are being read from TMEM.  Rows / columns beyond
+// the tensor's extent are clipped by the copy engine (the map carries the true M, N), so ragged edges need no predication.
+// The staged values stay in shared memory for the fused column reductions (which only read them).
+constexpr int CBOX = 16;                       // columns per store box = one tcgen05.ld.x16
+constexpr int CBOX_BYTES = BM * CBOX * 4;      // 8 KiB
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// wait for the issued TMEM loads; the "+r" operands tie the destination registers to the wait so that no use is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t r[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
+// float index of element (r, c) of the staged tile (boxes of 16 columns, 64-byte rows, SWIZZLE_64B)
+__device__ __forceinline__ int stage_idx(int r, int c) {
+  return (c >> 4) * (CBOX_BYTES / 4) + r * CBOX + ((((c >> 2) & 3) ^ ((r >> 1) & 3)) << 2) + (c & 3);
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_tma(uint8_t* smem, const float* s_bias, bool s_bias_on, uint32_t tmem_acc, int nkb, int m0,
+                                                int n0, int M, int N, const CUtensorMap* tmap_c, const TcEpilogue& ep) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = reinterpret_cast<float*>(smem);
+  constexpr int CSPLIT = (BN + 31) / 32 * 16;   // columns [0, CSPLIT): warps 0-3, [CSPLIT, BN): warps 4-7
+  const int grp = warp >> 2, q = warp & 3;
+  const int row = q * 32 + lane;
+  const int cbeg = grp * CSPLIT;
+  const int cnum = grp ? BN - CSPLIT : CSPLIT;
+  const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const int sw = (row >> 1) & 3;
+  // ReLU mask (dgrad through a ReLU: zero where mask_src <= 0), read in the TMEM register layout: one row per lane, 64 contiguous
+  // bytes per chunk.  (Reading the whole row up front as bits, 28 loads in flight per thread, measured SLOWER: with 220 KB of the
+  // SM's 256 KB carved out as shared memory the ~30 KB L1 thrashes on 32 rows x 7 lines per warp.)
+  const bool row_ok = m0 + row < M;
+  const float* mrow = (ep.mask_src && row_ok) ? ep.mask_src + (int64_t)(m0 + row) * ep.ldm + n0 : nullptr;
+  const bool mvec_ok = ep.mask_src && ((ep.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask_src) & 15) == 0) && ((n0 & 3) == 0);
+#pragma unroll 1
+  for (int c = 0; c < cnum; c += CBOX) {
+    const int col0 = cbeg + c;
+    if (n0 + col0 >= N) break;                  // whole box beyond the last column (uniform over the four warps of the group)
+    uint32_t a[16], b[16];
+    if (nkb > 0) {
+      tmem_ld16_issue(trow + (uint32_t)col0, a);
+      tmem_ld16_issue(trow + (uint32_t)(BN + col0), b);
+    }
+    float4 mk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mk[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (mrow) {                                 // the mask reads fly under the TMEM loads
+      if (mvec_ok && n0 + col0 + 15 < N) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const float4*>(mrow + col0 + 4 * j));
+      } else {
+        float* mw = reinterpret_cast<float*>(mk);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n0 + col0 + i < N) mw[i] = __ldg(mrow + col0 + i);
+      }
+    }
+    const float* mf = reinterpret_cast<const float*>(mk);
+    float v[16];
+    if (nkb > 0) {
+      tmem_ld_wait16(a);
+      asm volatile("" : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]),
+                        "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]) + __uint_as_float(b[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    float* dst = stage + (col0 >> 4) * (CBOX_BYTES / 4) + row * CBOX;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = v[4 * j + e];
+        if (s_bias_on) t += s_bias[col0 + 4 * j + e];   // one address per warp instruction: a broadcast
+        if (ep.relu) t = fmaxf(t, 0.f);
+        o[e] = mf[4 * j + e] > 0.f ? t : 0.f;
+      }
+      *reinterpret_cast<float4*>(dst + ((j ^ sw) << 2)) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    fence_async_smem();                          // this thread's generic-proxy stores -> visible to the copy engine
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+    if (q == 0 && lane == 0) {
+      tma_store_3d(tmap_c, smem_u32(stage + (col0 >> 4) * (CBOX_BYTES / 4)), n0 + col0, m0, (int)blockIdx.z);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (warp == 0) TC_TRACE(9);
+  // fused column reductions over the final tile (thread c owns output column n0 + c)
+  if (ep.hooks.colsum || ep.hooks.stats || ep.hooks.S) {
+    float* sS = stage + BM * BN;                 // [128][Q] slice of the per-row weights, behind the staged tile
+    const int rows_here = min(BM, M - m0);
+    if (ep.hooks.S)
+      for (int i = threadIdx.x; i < rows_here * ep.hooks.Q; i += NPRODUCER) sS[i] = ep.hooks.S[(int64_t)m0 * ep.hooks.Q + i];
+    asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
+    const int c = threadIdx.x;
+    if (c < BN && n0 + c < N) {
+      const int Q = ep.hooks.Q;
+      float s1 = 0.f;
+      double d1 = 0.0, d2 = 0.0;
+      float tq[16];
+#pragma unroll
+      for (int qq = 0; qq < 16; ++qq) tq[qq] = 0.f;
+      for (int r = 0; r < rows_here; ++r) {
+        const float v = stage[stage_idx(r, c)];
+        s1 += v;
+        if (ep.hooks.stats) { d1 += (double)v; d2 += (double)v * (double)v; }
+        if (ep.hooks.S) {
+#pragma unroll
+          for (int qq = 0; qq < 16; ++qq)
+            if (qq < Q) tq[qq] = fmaf(sS[r * Q + qq], v, tq[qq]);
+        }
+      }
+      if (ep.hooks.colsum) atomicAdd(&ep.hooks.colsum[n0 + c], s1);
+      if (ep.hooks.stats) {
+        atomicAdd(&ep.hooks.stats[n0 + c], d1);
+        atomicAdd(&ep.hooks.stats[(int64_t)N + n0 + c], d2);
+      }
+      if (ep.hooks.S) {
+#pragma unroll
+        for (int qq = 0; qq < 16; ++qq)
+          if (qq < Q)
+            atomicAdd(qq < ep.hooks.q_split ? &ep.hooks.gT[(int64_t)qq * ep.hooks.ldt + n0 + c]
+                                            : &ep.hooks.gT2[(int64_t)(qq - ep.hooks.q_split) * ep.hooks.ldt + n0 + c], tq[qq]);
+      }
+    }
+  }
+  // shared memory must stay intact until the copy engine has read every box this thread submitted
+  if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <bool A_MN, bool B_MN, int BN, bool PAIR>
 __global__ void __launch_bounds__(T_NTHREADS, 1)
-k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
+k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, int tma_store, float* __restrict__ C,
                   int64_t ldc, int M, int N, int K, int k_per_split, TcEpilogue ep) {
   static_assert(!PAIR || (!A_MN && !B_MN && BN % 32 == 0), "the pair variant takes K-major operands; UMMA N % 16 == 0 at M = 256");
   static_assert(BN % 16 == 0 && BN <= 256 && (!B_MN || BN % 32 == 0), "UMMA N % 16 == 0 at M = 128; MN-major B boxes hold 32 rows");
@@ -344,7 +498,8 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tc_fence_after();
     if (warp == 0) TC_TRACE(6);
 #ifndef PGNN_UB_NO_EPILOGUE
-    tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
+    if (tma_store) tc_epilogue_tma<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, &tmap_c, ep);
+    else tc_epilogue<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, C + (int64_t)blockIdx.z * ep.split_stride, ldc, ep);
     if (ep.fold_counter) splitk_fold_in_kernel<BN>(C, ldc, m0, n0, M, N, ep);
 #endif
     if (warp == 0) TC_TRACE(7);
@@ -420,6 +575,54 @@ bool cached_map(CUtensorMap* out, const float* base, bool mn, int64_t R, int64_t
   return true;
 }
 
+// Output tensor map of the TMA-store epilogue: global tensor [splits][M][N] fp32 (row stride ldc, split stride split_stride
+// floats), box [1][128 rows][16 cols], SWIZZLE_64B.  The extents are the true ones: the copy engine clips ragged edge tiles.
+struct MapCKey {
+  const void* base; int64_t M, N, ldc, splits, stride;
+  bool operator==(const MapCKey& o) const {
+    return base == o.base && M == o.M && N == o.N && ldc == o.ldc && splits == o.splits && stride == o.stride;
+  }
+};
+struct MapCKeyHash {
+  size_t operator()(const MapCKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    for (int64_t v : {k.M, k.N, k.ldc, k.splits, k.stride}) h = h * 1000003u ^ (size_t)v;
+    return h;
+  }
+};
+bool cached_map_c(CUtensorMap* out, const float* base, int64_t M, int64_t N, int64_t ldc, int64_t splits, int64_t split_stride) {
+  static std::unordered_map<MapCKey, CUtensorMap, MapCKeyHash> cache;
+  static std::mutex mu;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  if (splits <= 1) { splits = 1; split_stride = M * ldc; }
+  const MapCKey key{base, M, N, ldc, splits, split_stride};
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  alignas(64) CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+  cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)split_stride * 4};
+  cuuint32_t box[3] = {(cuuint32_t)CBOX, (cuuint32_t)BM, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return true;
+}
+// PGNN_TMA_STORE=0: the st.global epilogue of tc_common.cuh (development switch / A-B measurement)
+bool tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGNN_TMA_STORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // CTA pairs (cta_group::2) for the K-major x K-major GEMMs: opt-in with PGNN_PAIR=1.  Measured on B200 (tools/check_tc.py,
 // tools/trace_tc.py): numerically identical to the single-CTA kernel, but a 32-deep block costs 1.14-1.17 us whatever the tile
 // width (BN = 224 and 128 alike, 1.0 us for a lone cluster on an idle GPU, with or without the proxy fence / cluster-scope
@@ -443,8 +646,14 @@ int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* 
   // pairs of row tiles share the column tile; an odd tile count gets an all-padding partner, which must not cost a wave
   const int64_t ctas = (int64_t)mt * nt, ctas_pair = (int64_t)(mt + (mt & 1)) * nt;
   const bool pair = kPairable && pair_enabled() && splits == 1 && mt >= 2 && ceil_div(ctas_pair, kNumSMs) <= ceil_div(ctas, kNumSMs);
-  alignas(64) CUtensorMap ma, mb;
+  alignas(64) CUtensorMap ma, mb, mc;
   if (!cached_map(&ma, A, A_MN, M, K, lda, BM) || !cached_map(&mb, B, B_MN, N, K, ldb, pair ? BN / 2 : BN)) return PGNN_EUNSUPPORTED;
+  // TMA-store epilogue whenever the output is a plain (non-atomic) store with 16-byte aligned rows
+  int tma_store = 0;
+  if (tma_store_enabled() && !ep.atomic && !ep.fold_counter && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+      (splits == 1 || (ep.split_stride & 3) == 0) && cached_map_c(&mc, C, M, N, ldc, splits, ep.split_stride))
+    tma_store = 1;
+  if (!tma_store) mc = ma;  // unused by the kernel, but a kernel parameter must be a valid object
   static bool configured = false;
   if (!configured) {
     PGNN_CUDA(cudaFuncSetAttribute(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -458,13 +667,13 @@ int launch_tma(const float* A, int64_t lda, const float* B, int64_t ldb, float* 
     if (pair) {
       dim3 grid((unsigned)(mt + (mt & 1)), (unsigned)nt, 1u);
       PGNN_CUDA(pgnn_launch_cluster_x(k_gemm_3xtf32_tma<A_MN, B_MN, BN, true>, dim3(grid), dim3(T_NTHREADS), TmaCfg<BN, true>::SMEM, st, 2u,
-                                      ma, mb, C, ldc, M, N, K, k_per_split, ep));
+                                      ma, mb, mc, tma_store, C, ldc, M, N, K, k_per_split, ep));
       PGNN_LAUNCH_CHECK();
       return PGNN_OK;
     }
   }
   dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
-  PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, dim3(grid), dim3(T_NTHREADS), TmaCfg<BN, false>::SMEM, st, ma, mb, C, ldc, M, N,
+  PGNN_CUDA(pgnn_launch(k_gemm_3xtf32_tma<A_MN, B_MN, BN, false>, dim3(grid), dim3(T_NTHREADS), TmaCfg<BN, false>::SMEM, st, ma, mb, mc, tma_store, C, ldc, M, N,
                         K, k_per_split, ep));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;

@@ -53,57 +53,73 @@ def _unpack(views, params):
 
 
 class P2PAllReduce:
-    """A symmetric fp32 buffer of `numel` elements plus the flag words of `pgnn_allreduce_p2p`.
+    """Symmetric fp32 buffers of `numel` elements plus the flag words of the library's NVLink all-reduces.
 
-    `nvls=True` (or PGNN_ALLREDUCE=nvls; EXPERIMENTAL, not yet measured) routes `run` through `pgnn_allreduce_nvls`: the
-    NVSwitch performs the sum (multimem.ld_reduce on the buffer's multicast mapping).  Falls back to the peer-load kernels
-    when the allocation has no multicast mapping."""
+    mode (argument, else PGNN_ALLREDUCE, else "fused"):
+      "fused"   one kernel, out of place (`pgnn_allreduce_fused`): gradients are written into `buf`, the mean lands in `out`
+      "nvls"    the same kernel with the NVSwitch doing the sum (multimem.ld_reduce / multimem.st on the multicast mappings);
+                falls back to "fused" when the allocation has no multicast mapping
+      "p2p"     round 1's five-launch two-shot exchange, in place (`pgnn_allreduce_p2p`): `out` is `buf`
+    `run()` returns the buffer that holds the result."""
 
-    FLAG_FLOATS = 64  # 256 bytes in front of the data: keeps the data 16-byte aligned; words [0,32) p2p flags, [32,64) nvls flags
+    FLAG_FLOATS = 128  # 512 bytes in front of the data (keeps it 16-byte aligned): words [0,32) p2p, [32,64) old nvls, [64,128) fused
 
-    def __init__(self, numel, device, group=None, nvls=None):
+    def __init__(self, numel, device, group=None, mode=None):
         import os
         import torch.distributed._symmetric_memory as symm
         from ._cabi import lib
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world, self.numel = dist.get_rank(group), dist.get_world_size(group), int(numel)
-        if nvls is None:
-            nvls = os.environ.get("PGNN_ALLREDUCE", "") == "nvls"
+        mode = mode or os.environ.get("PGNN_ALLREDUCE", "") or "fused"
+        if mode not in ("fused", "nvls", "p2p"):
+            raise ValueError("PGNN_ALLREDUCE must be fused, nvls or p2p")
         quantum = 4 * self.world
-        self.padded = (self.numel + quantum - 1) // quantum * quantum  # the nvls kernel works on whole float4s per rank
-        self.sym = symm.empty(self.FLAG_FLOATS + self.padded, dtype=torch.float32, device=device)
+        self.padded = (self.numel + quantum - 1) // quantum * quantum  # whole float4s per rank (the multimem path needs them)
+        two = mode != "p2p"
+        self.sym = symm.empty(self.FLAG_FLOATS + (2 if two else 1) * self.padded, dtype=torch.float32, device=device)
         self.sym.zero_()
         hdl = symm.rendezvous(self.sym, group)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         self._hdl = hdl
-        self.buf = self.sym[self.FLAG_FLOATS:self.FLAG_FLOATS + self.numel]
+        F = self.FLAG_FLOATS
+        self.buf = self.sym[F:F + self.numel]
+        self.out = self.sym[F + self.padded:F + self.padded + self.numel] if two else self.buf
         self.flag_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
-        self.buf_ptrs = torch.tensor([p + 4 * self.FLAG_FLOATS for p in ptrs], dtype=torch.int64, device=device)
+        self.buf_ptrs = torch.tensor([p + 4 * F for p in ptrs], dtype=torch.int64, device=device)
+        self.out_ptrs = torch.tensor([p + 4 * (F + self.padded) for p in ptrs], dtype=torch.int64, device=device)
         nscratch = lib.pgnn_allreduce_p2p_scratch_floats(self.numel, self.world)
         self.scratch = torch.empty(max(int(nscratch), 4), dtype=torch.float32, device=device)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=device)
         self.epoch = 0
-        self.mc_buf = None
-        if nvls:
-            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if getattr(hdl, "has_multicast_support", lambda *a: True) else 0
+        self.mc_in = self.mc_out = 0
+        if mode == "nvls":
+            mc = 0
+            try:
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            except Exception:
+                mc = 0
             if mc and self.world <= 32:
-                self.mc_buf = mc + 4 * self.FLAG_FLOATS
-                self.nvls_flag_ptrs = torch.tensor([p + 128 for p in ptrs], dtype=torch.int64, device=device)
-        self.transport = "nvls" if self.mc_buf else "p2p"
+                self.mc_in, self.mc_out = mc + 4 * F, mc + 4 * (F + self.padded)
+            else:
+                mode = "fused"
+        self.transport = mode
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's zeroed flag words are in place before anyone signals
 
     def run(self, scale=1.0):
         from ._cabi import check, lib
         st = torch.cuda.current_stream(self.sym.device).cuda_stream
-        if self.mc_buf:
-            check(lib.pgnn_allreduce_nvls(self.mc_buf, self.nvls_flag_ptrs.data_ptr(), self.rank, self.world, self.padded, float(scale),
-                                          self.epoch, st), "pgnn_allreduce_nvls")
-        else:
+        if self.transport == "p2p":
             check(lib.pgnn_allreduce_p2p(self.buf_ptrs.data_ptr(), self.flag_ptrs.data_ptr(), self.rank, self.world, self.numel,
                                          float(scale), self.scratch.data_ptr(), self.scratch.numel(), self.epoch, st),
                   "pgnn_allreduce_p2p")
+        else:
+            n = self.padded if self.mc_in else self.numel
+            check(lib.pgnn_allreduce_fused(self.buf_ptrs.data_ptr(), self.out_ptrs.data_ptr(), self.flag_ptrs.data_ptr(),
+                                           self.mc_in or None, self.mc_out or None, self.counter.data_ptr(), self.rank, self.world, n,
+                                           float(scale), self.epoch, st), "pgnn_allreduce_fused")
         self.epoch += 1
-        return self.buf
+        return self.out
 
 
 class GradAllReducer:
@@ -141,7 +157,7 @@ class GradAllReducer:
         if backend != "nccl" and on_cuda and dist.get_world_size(group) > 1:
             try:
                 self._setup_p2p(all_params[0].device)
-                self.backend = self.p2p.transport  # "p2p", or "nvls" when opted in
+                self.backend = self.p2p.transport  # "fused" (default), "nvls" or "p2p"
             except Exception as e:  # no peer access / symmetric memory unavailable on this box
                 if backend == "p2p":
                     raise
@@ -164,27 +180,43 @@ class GradAllReducer:
             offs.append(tot)
             tot += pad4(n)
         self.p2p = P2PAllReduce(tot, device, self.group)
-        self.regions = [self.p2p.buf[o:o + n] for o, n in zip(offs[:-1], src_sizes)]
-        self.region_views = [[v.view_as(p) for v, p in zip(r.split([p.numel() for p in src()[1]]), src()[1])]
-                             for src, r in zip(self.flat_sources, self.regions)]
+        inb, outb = self.p2p.buf, self.p2p.out
+        self.in_place = outb.data_ptr() == inb.data_ptr()
+        split = lambda buf, src: [v.view_as(p) for v, p in zip(buf.split([p.numel() for p in src()[1]]), src()[1])]
+        self.regions = [inb[o:o + n] for o, n in zip(offs[:-1], src_sizes)]            # where the backward writes
+        self.out_regions = [outb[o:o + n] for o, n in zip(offs[:-1], src_sizes)]       # where the mean lands
+        self.region_views = [split(r, src) for src, r in zip(self.flat_sources, self.regions)]
+        self.out_views = [split(r, src) for src, r in zip(self.flat_sources, self.out_regions)]
         for src, region in zip(self.flat_sources, self.regions):
             if hasattr(src, "bind"):
                 src.bind(region)
-        self.flat = self.p2p.buf[offs[-1]:offs[-1] + sum(self.sizes)] if self.params else None
+        self.flat = inb[offs[-1]:offs[-1] + sum(self.sizes)] if self.params else None
+        self.flat_out = outb[offs[-1]:offs[-1] + sum(self.sizes)] if self.params else None
         if self.params:
             self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+            self.views_out = [v.view_as(p) for v, p in zip(self.flat_out.split(self.sizes), self.params)]
 
     def _all_reduce_p2p(self, inv):
+        """Gradients -> the symmetric input buffer (the bound encoders' backward already wrote them there) -> one exchange ->
+        every p.grad refers to / is refreshed from the buffer that holds the mean.  Out of place (the default one-kernel
+        exchange) the encoders' `p.grad` are RE-POINTED to the views of the output buffer: no copy in either direction."""
         after = []
-        for src, region, views in zip(self.flat_sources, self.regions, self.region_views):
+        for src, region, views, oregion, oviews in zip(self.flat_sources, self.regions, self.region_views, self.out_regions, self.out_views):
             flat, ps = src()
             if _flat_is_live(flat, ps):
                 if flat.data_ptr() != region.data_ptr():  # live, but somewhere else: one bulk copy each way
                     region.copy_(flat)
-                    after.append(lambda flat=flat, region=region: flat.copy_(region))
+                    after.append(lambda flat=flat, oregion=oregion: flat.copy_(oregion))
+                elif not self.in_place:
+                    def repoint(src=src, ps=ps, oviews=oviews, oregion=oregion):
+                        for p, v in zip(ps, oviews):
+                            p.grad = v
+                        if hasattr(src, "set_flat"):
+                            src.set_flat(oregion)
+                    after.append(repoint)
             else:  # e.g. gradients accumulated over several backward passes: the parameters' .grad are the truth
                 _pack(views, ps)
-                after.append(lambda views=views, ps=ps: _unpack(views, ps))
+                after.append(lambda oviews=oviews, ps=ps: _unpack(oviews, ps))
         if self.params:
             _pack(self.views, self.params)
         self.p2p.run(inv if self.scale else 1.0)
@@ -194,8 +226,8 @@ class GradAllReducer:
         for fn in after:
             fn()
         if self.params:
-            _unpack(self.views, self.params)
-        return self.flat
+            _unpack(self.views_out, self.params)
+        return self.flat_out
 
     # ---- torch.distributed transport --------------------------------------------------------------------------------
     def _on_grad(self, _param):
@@ -269,6 +301,11 @@ def encoder_flat_source(gnn):
         plan = gnn._fused_plan()
         if plan is not None:
             plan.live_forwards = 0
+    def set_flat(buffer):
+        plan = gnn._fused_plan()
+        if plan is not None:
+            plan.last_flat_grad = buffer
     src.bind = bind
     src.step_done = step_done
+    src.set_flat = set_flat
     return src

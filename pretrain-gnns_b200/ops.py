@@ -679,6 +679,60 @@ class ChemGinPlan:
         self.last_ws = None
 
 
+def _grow_only(plan, need):
+    """Workspace size actually requested from the allocator: the largest need seen so far plus headroom, rounded to 16 MiB.  Batches
+    differ by a few percent in N and E; asking for exactly `need` makes every new maximum a cudaMalloc (milliseconds, and a device
+    synchronisation) in the middle of training, whereas one size per plan is served from the caching allocator's free list."""
+    if need < 0:
+        return need
+    cur = getattr(plan, "_ws_alloc", 0)
+    if need > cur:
+        cur = ((need + need // 16) + (16 << 20) - 1) // (16 << 20) * (16 << 20)
+        plan._ws_alloc = cur
+    return cur
+
+
+
+def _deliver_flat_grads(plan, ctx, run):
+    """Shared tail of the whole-encoder backwards: pick the flat gradient buffer, run the C backward into it (`run(flat)`), and hand
+    the per-parameter views to autograd.
+
+    Fast path (the normal training step: one live forward, no parameter holds a gradient yet, every parameter is a leaf that
+    wants one): the gradients land in a buffer that persists across steps (the caller's `plan.grad_buffer`, e.g. NVLink-symmetric
+    memory, else one the plan owns) and each `p.grad` is set to its cached view directly; autograd gets None for the
+    parameters.  That skips 40-odd AccumulateGrad nodes and as many split/view calls per step (~250 us of host time, more than
+    the C side spends enqueueing the whole backward).  Hooks on the parameters / DDP are not supported on this path: set
+    `plan.direct_grads = False` to have every gradient returned through autograd instead."""
+    params = plan.params
+    sole = plan.live_forwards == 1
+    plan.live_forwards = max(plan.live_forwards - 1, 0)
+    needs = ctx.needs_input_grad[5:]
+    clean = sole and all(p.grad is None for p in params)
+    if clean and getattr(plan, "direct_grads", True) and all(needs) and all(p.is_leaf for p in params):
+        flat = plan.grad_buffer
+        if flat is None:
+            flat = getattr(plan, "_own_flat", None)
+            if flat is None or flat.device != ctx.x.device:
+                flat = plan._own_flat = torch.empty(plan.total, dtype=torch.float32, device=ctx.x.device)
+        cache = getattr(plan, "_views", None)
+        if cache is None or cache[0] != flat.data_ptr():
+            cache = plan._views = (flat.data_ptr(), [v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)])
+        run(flat)
+        plan.last_flat_grad = flat
+        for p, v in zip(params, cache[1]):
+            p.grad = v
+        return (None,) * (5 + len(params))
+    if plan.grad_buffer is not None and clean:
+        flat = plan.grad_buffer
+    else:
+        flat = torch.empty(plan.total, dtype=torch.float32, device=ctx.x.device)
+    run(flat)
+    plan.last_flat_grad = flat
+    grads = [v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)]
+    return (None, None, None, None, None) + tuple(gr if need else None for gr, need in zip(grads, needs))
+
+
+
 class _ChemGinEncoder(Function):
     @staticmethod
     def forward(ctx, plan, x, edge_index, edge_attr, training, *params):
@@ -702,7 +756,7 @@ class _ChemGinEncoder(Function):
         rm = plan.BnArr(*[b.running_mean.data_ptr() for b in bns])
         rv = plan.BnArr(*[b.running_var.data_ptr() for b in bns])
         nbt = plan.BnArr(*[b.num_batches_tracked.data_ptr() for b in bns])
-        wsb = lib.pgnn_chem_gin_workspace_bytes(N, E, L, D)
+        wsb = _grow_only(plan, lib.pgnn_chem_gin_workspace_bytes(N, E, L, D))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         out = torch.empty(N, D, dtype=torch.float32, device=dev)
         mom = bns[0].momentum if bns[0].momentum is not None else 0.1
@@ -725,17 +779,11 @@ class _ChemGinEncoder(Function):
         plan = ctx.plan
         N, E, L, D = ctx.dims
         g = _f32(g)
-        sole = plan.live_forwards == 1
-        plan.live_forwards = max(plan.live_forwards - 1, 0)
-        if plan.grad_buffer is not None and sole and all(p.grad is None for p in plan.params):
-            flat = plan.grad_buffer
-        else:
-            flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
-        check(lib.pgnn_chem_gin_backward(ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), N, E, L, D, _precision, _p(flat), _p(ctx.ws),
-                                         ctx.wsb, _st()), "chem_gin_backward")
-        plan.last_flat_grad = flat
-        grads = [v if len(s) == 1 else v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)]
-        return (None, None, None, None, None) + tuple(gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[5:]))
+
+        def run(flat):
+            check(lib.pgnn_chem_gin_backward(ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), N, E, L, D, _precision, _p(flat), _p(ctx.ws),
+                                             ctx.wsb, _st()), "chem_gin_backward")
+        return _deliver_flat_grads(plan, ctx, run)
 
 
 def chem_gin_relu_masks(plan: ChemGinPlan, gnn):
@@ -825,7 +873,7 @@ class _ChemConvEncoder(Function):
         rm = plan.BnArr(*[b.running_mean.data_ptr() for b in bns])
         rv = plan.BnArr(*[b.running_var.data_ptr() for b in bns])
         nbt = plan.BnArr(*[b.num_batches_tracked.data_ptr() for b in bns])
-        wsb = lib.pgnn_chem_conv_workspace_bytes(plan.conv, N, E, L, D)
+        wsb = _grow_only(plan, lib.pgnn_chem_conv_workspace_bytes(plan.conv, N, E, L, D))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         out = torch.empty(N, D, dtype=torch.float32, device=dev)
         mom = bns[0].momentum if bns[0].momentum is not None else 0.1
@@ -846,17 +894,11 @@ class _ChemConvEncoder(Function):
         plan = ctx.plan
         N, E, L, D = ctx.dims
         g = _f32(g)
-        sole = plan.live_forwards == 1
-        plan.live_forwards = max(plan.live_forwards - 1, 0)
-        if plan.grad_buffer is not None and sole and all(p.grad is None for p in plan.params):
-            flat = plan.grad_buffer
-        else:
-            flat = torch.empty(plan.total, dtype=torch.float32, device=g.device)
-        check(lib.pgnn_chem_conv_backward(plan.conv, ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), _p(ctx.ea), N, E, L, D, _precision, _p(flat),
-                                          _p(ctx.ws), ctx.wsb, _st()), "chem_conv_backward")
-        plan.last_flat_grad = flat
-        grads = [v.view(s) for v, s in zip(flat.split(plan.sizes), plan.shapes)]
-        return (None, None, None, None, None) + tuple(gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[5:]))
+
+        def run(flat):
+            check(lib.pgnn_chem_conv_backward(plan.conv, ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), _p(ctx.ea), N, E, L, D, _precision,
+                                              _p(flat), _p(ctx.ws), ctx.wsb, _st()), "chem_conv_backward")
+        return _deliver_flat_grads(plan, ctx, run)
 
 
 def chem_conv_encoder(plan: ChemConvPlan, x, edge_index, edge_attr, training: bool):

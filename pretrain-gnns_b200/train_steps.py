@@ -55,7 +55,12 @@ class _Step:
     modules: list
 
     def parameters(self):
-        return [p for m in self.modules for p in m.parameters()]
+        # the module set of a step is fixed: walk it once (nn.Module.parameters() re-traverses every submodule on each call,
+        # ~200 us of host time per training step when zero_grad does it)
+        ps = getattr(self, "_params", None)
+        if ps is None:
+            ps = self._params = [p for m in self.modules for p in m.parameters()]
+        return ps
 
     def zero_grad(self):
         for p in self.parameters():

@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mode):
     sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PGNN_ALLREDUCE=mode)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     syn = importlib.import_module("pretrain-gnns_b200.synthetic")
@@ -44,41 +44,53 @@ def _worker(rank, world, port, out):
         red.all_reduce_mean()
         torch.cuda.synchronize()
         res["steps"].append({"want": [g.cpu() for g in want], "got": [p.grad.detach().cpu().clone() for p in params],
-                             "in_place": gnn._fused_plan().last_flat_grad.data_ptr() == red.regions[0].data_ptr()})
+                             # no packing copy: the encoder wrote into the symmetric input region and (out-of-place exchange)
+                             # its p.grad now refer to the output region
+                             "in_place": gnn._fused_plan().last_flat_grad.data_ptr() == (red.regions[0] if red.in_place else red.out_regions[0]).data_ptr()
+                                         and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(gnn._fused_plan().params, red.region_views[0] if red.in_place else red.out_views[0]))})
     red.close()
     torch.save(res, os.path.join(out, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
-def _oracle_shard_grads(state, head, rank, step):
-    """Gradients of one rank's shard of one step from the CPU oracle (fp64): SURVEY.md 8(e) — the reduced gradient must
+def _oracle_shard_grads(state, head, rank, step, dtype=torch.float64):
+    """Gradients of one rank's shard of one step from the CPU oracle: SURVEY.md 8(e) — the reduced gradient must
     equal the MEAN of the per-shard oracle gradients (BatchNorm statistics are per rank, like DDP without SyncBN)."""
     sys.path.insert(0, ROOT)
     from oracle import gnn_oracle as O
     syn = importlib.import_module("pretrain-gnns_b200.synthetic")
     b = syn.zinc_batch(8, 100 * step + rank)
-    L = O.leaf_params(state, torch.float64)
-    W, bias = head["weight"].double().requires_grad_(True), head["bias"].double().requires_grad_(True)
+    L = O.leaf_params(state, dtype)
+    W, bias = head["weight"].to(dtype).requires_grad_(True), head["bias"].to(dtype).requires_grad_(True)
     rep = O.chem_gnn(L, b["x"], b["edge_index"], b["edge_attr"], 3, "gin", True)
     torch.nn.functional.linear(rep, W, bias).square().mean().backward()
-    return [L[k].grad for k in state if k in L and L[k].requires_grad] + [W.grad, bias.grad]
+    return [L[k].grad.double() for k in state if k in L and L[k].requires_grad] + [W.grad.double(), bias.grad.double()]
 
 
-def test_p2p_allreduce_matches_nccl_mean(tmp_path):
+@pytest.mark.parametrize("mode", ["fused", "p2p", "nvls"])
+def test_p2p_allreduce_matches_nccl_mean(tmp_path, mode):
+    """fused = the one-kernel out-of-place exchange (default), p2p = round 1's five-launch in-place exchange, nvls = the one-kernel
+    exchange with multimem.ld_reduce / multimem.st (reported as "fused" when the allocation has no multicast mapping)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    world, port = 2, 29100 + os.getpid() % 2000
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    world, port = 2, 29100 + os.getpid() % 2000 + {"fused": 0, "p2p": 1, "nvls": 2}[mode]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), mode), nprocs=world, join=True)
     r = [torch.load(os.path.join(tmp_path, f"r{k}.pt")) for k in range(world)]
-    assert r[0]["backend"] in ("p2p", "nvls")
+    assert r[0]["backend"] == mode or (mode == "nvls" and r[0]["backend"] == "fused")
+    print("all-reduce transport:", r[0]["backend"])
     # step 0 (fresh gradients, parameters still at their initial values on both ranks): reduced gradient == mean of the
     # two shards' oracle gradients
     o0, o1 = (_oracle_shard_grads(r[0]["state"], r[0]["head"], k, 0) for k in range(world))
+    f0, f1 = (_oracle_shard_grads(r[0]["state"], r[0]["head"], k, 0, torch.float32) for k in range(world))
     gmax = max(float(((a + b) / 2).abs().max()) for a, b in zip(o0, o1))
-    for a, b, got in zip(o0, o1, r[0]["steps"][0]["got"]):
+    for a, b, a32, b32, got in zip(o0, o1, f0, f1, r[0]["steps"][0]["got"]):
         want = (a + b) / 2
         scale = max(float(want.abs().max()), 1e-3 * gmax)
-        assert float((got.double() - want).abs().max()) <= 2e-4 * scale
+        # the bar of the single-GPU parity tests (tests/golden_util.py): per tensor, on its own scale, 3x the oracle's own
+        # fp32-vs-fp64 discrepancy (train-mode BatchNorm over a 190-node shard makes fp32 gradients ill-conditioned)
+        e_ref = float(((a32 + b32) / 2 - want).abs().max()) / scale
+        err = float((got.double() - want).abs().max()) / scale
+        assert err <= max(5e-5, 3 * e_ref), (err, e_ref)
     assert [s["in_place"] for s in r[0]["steps"]] == [True, True, False, True]
     for s0, s1 in zip(r[0]["steps"], r[1]["steps"]):
         for w, g0, g1 in zip(s0["want"], s0["got"], s1["got"]):
