@@ -116,10 +116,15 @@ class ClockSampler:
         nv = self.nv
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        # the maximum clock is a constant of the board and nvmlDeviceGetMaxClockInfo is the one slow call here (1.5-19 ms measured,
+        # tools/diag_nvml.py, against 3-8 us for the other two): query it once, before the timed region
+        try:
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
         while not self.stop:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
@@ -132,6 +137,8 @@ class ClockSampler:
             time.sleep(0.05)
 
     def __enter__(self):
+        if os.environ.get("PGNN_BENCH_NO_CLOCKS") == "1":   # diagnostic: no sampler thread at all (the line then carries no clocks)
+            return self
         if self.nv is not None:
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
@@ -364,8 +371,16 @@ def run_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         ticket, acc = None, 0.0
         host_t = []
+        prof_step = int(os.environ.get("PGNN_BENCH_PROFILE_STEP", "-1")) if e2e else -1   # diagnostic: cProfile ONE iteration
         for i in range(args.steps):
             host_t.append(time.perf_counter())
+            if i == prof_step:
+                import cProfile
+                pr = cProfile.Profile(); pr.enable()
+            elif i == prof_step + 1 and prof_step >= 0:
+                import io, pstats
+                pr.disable(); buf = io.StringIO(); pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(12)
+                print(buf.getvalue(), file=sys.stderr, flush=True)
             flush.zero_()  # L2 flush, outside the per-step event pair
             ev[i][0].record()
             if e2e:

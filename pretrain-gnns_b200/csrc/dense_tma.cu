@@ -28,6 +28,7 @@
 // PGNN_UB_NO_EPILOGUE.  Results are garbage; the timings isolate what each role costs under full-chip load.
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -514,6 +515,342 @@ k_gemm_3xtf32_tma(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+// ---- fused GIN layer front half: neighbour gather + GEMM1 in one kernel ------------------------------------------------------
+// chem/model.py:37-55: aggr[i] = sum_{k: target(k) = i} act(x[source(k)]) + act(x[i]) + S[i,:].T (edge-feature embedding as a
+// 9-bin dot product, neighbour reduction over the target-bucketed edge list, self-loop last, the previous layer's BatchNorm +
+// ReLU applied on load) and z1 = relu(aggr . W1^T + b1).
+//
+// The gridDim.x CTAs that own the column tiles of ONE 128-row tile work as a team.  Phase 1: they split the row tile's reduction
+// blocks among themselves (block kb goes to CTA kb mod gridDim.x); the 8 producer warps of each gather their blocks — a thread
+// owns four (row, 16-byte chunk) items of a [128 x 32] block, loads the self row and up to four neighbour rows per item with
+// every load in flight, reduces in edge order (bit-identical to k_aggregate_fwd) — and store the rows to `aggr` (the backward's
+// weight-gradient GEMM needs them anyway).  Meanwhile the TMA warp already streams the first weight tiles.  A per-row-tile
+// arrival counter (red.release.gpu after a generic->async proxy fence; the TMA thread spins with ld.acquire.gpu, time-bounded)
+// publishes the tile inside the team; phase 2 is the main loop of k_gemm_3xtf32_tma with the A boxes loaded from the
+// just-written, L2-resident rows.
+//
+// Why not gather straight into the swizzled operand stage (the first version of this kernel did): each of the three column
+// tiles then repeats the whole gather, and 3 x 30 MB of L2 reads per layer made the fused kernel SLOWER than gather + GEMM
+// (58 vs 43 us, measured).  Splitting the gather over the team keeps the L2 traffic of the unfused pair and removes what
+// separated them: a launch, a full-chip drain and refill, and the GEMM prologue now overlaps the gather.
+// Why a counter and not a thread-block cluster (the second version): clusters are placed inside one GPC, and only 45 clusters of
+// three 221 KB CTAs fit this chip at once (cudaOccupancyMaxActiveClusters) while the B = 256 batch needs 47 - a second wave.
+// A team's CTAs are adjacent in launch order (x fastest), so they become resident together; a CTA whose team mates are not
+// resident yet only delays its A loads (every wait is time-bounded and traps instead of hanging).
+struct GinGather {
+  const float* x; int64_t ldx;                     // input rows [M, K], pre-affine
+  const float* in_scale; const float* in_shift;    // explicit affine (or null)
+  PgnnBnFold fold;                                 // or: derive it from the producer's BatchNorm sums (fold.acc != null)
+  int relu;
+  const int* rowptr; const int* nbr;               // edges bucketed by target
+  const float* S; int Q; const float* T; const float* T2; int q_split;   // per-node edge-feature summary and the stacked tables
+  float* aggr; int64_t lda;                        // the aggregated rows (output of phase 1, A operand of phase 2)
+};
+
+constexpr int G_KPAD = 320;       // K <= 320 (affine / table rows staged in shared memory)
+constexpr int G_MAXQ = 9;
+constexpr int G_STAGING = (2 * G_KPAD + BM * G_MAXQ + G_MAXQ * G_KPAD) * 4;  // lives in the (idle) lo stages
+
+__device__ __forceinline__ float4 g_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// 16-byte load that does not allocate in L1 (ld.global.cg), predicated without a branch.  This kernel carves 221 KB of the SM's
+// 256 KB out as shared memory: ~30 KB of L1 = ~240 lines, and an L1-allocating load holds a line while it is in flight, so the
+// 5120 row loads a CTA issues per reduction block were throttled to what 240 lines turn over (measured: 5 us per block, 1.5 TB/s
+// chip-wide, the same data the stand-alone gather moves at 3.8 TB/s with the whole 256 KB as L1).
+__device__ __forceinline__ float4 g_ldcg4(const float* p, bool pred) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ float4 g_act(float4 v, float4 sc, float4 sh, bool affine, bool relu) {
+  if (affine) { v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w); }
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  return v;
+}
+__device__ __forceinline__ void g_add4(float4& a, float4 v) {
+  a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
+}
+
+// development stamps of CTA (0,0) of the fused kernel (pgnn_debug_gather_trace reads them)
+__device__ unsigned long long g_gather_trace[16];
+#define G_TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) g_gather_trace[slot] = globaltimer_ns(); } while (0)
+
+template <int BN>
+__global__ void __launch_bounds__(T_NTHREADS, 1)
+k_gin_gather_gemm(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, TcEpilogue ep, GinGather g, unsigned int* tile_ctr) {
+  static_assert(BN % 16 == 0 && BN <= 256, "UMMA N % 16 == 0 at M = 128");
+  using Cfg = TmaCfg<BN, false>;
+  constexpr int NRAW = Cfg::NRAW, T_NLO = Cfg::NLO;
+  static_assert(T_NLO * Cfg::STAGE >= G_STAGING, "the gather's staging area lives in the lo stages");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], lo_full[T_NLO], lo_empty[T_NLO], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[BN];
+
+  auto raw = [&](int kb) { return smem + (kb % NRAW) * Cfg::STAGE; };
+  auto lo = [&](int kb) { return smem + (NRAW + kb % T_NLO) * Cfg::STAGE; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (K + TBK - 1) / TBK;
+  const bool s_bias_on = ep.bias != nullptr;
+  if (warp == 0) G_TRACE(0);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < NRAW; ++s) {
+      mbar_init(smem_u32(&raw_full[s]), 1);
+      mbar_init(smem_u32(&raw_empty[s]), 1);
+    }
+    for (int s = 0; s < T_NLO; ++s) {
+      mbar_init(smem_u32(&lo_full[s]), NPRODUCER / 32);
+      mbar_init(smem_u32(&lo_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&acc_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_s;
+  constexpr uint32_t idesc = umma_idesc(BM, BN, false, false);
+  const uint32_t crank = blockIdx.x, csize = gridDim.x;   // this CTA's place in the row tile's team
+  pdl_prologue();
+  if (warp == 0) G_TRACE(1);
+
+  if (warp == 9) {
+    // ---------------- TMA producer ----------------
+    const int pre = nkb < NRAW ? nkb : NRAW;
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+      for (int kb = 0; kb < pre; ++kb) {   // the weight tiles do not depend on the gather: stream them under phase 1
+        mbar_expect_tx(smem_u32(&raw_full[kb]), Cfg::STAGE);
+        tma_load_2d(smem_u32(raw(kb)) + Cfg::A_BYTES, &tmap_b, smem_u32(&raw_full[kb]), kb * TBK, n0);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      // every CTA of the team has stored (and fenced) its share of the row tile
+      const unsigned int* ctr = tile_ctr + blockIdx.y;
+      const uint64_t t0 = globaltimer_ns();
+      for (uint32_t it = 0;; ++it) {
+        unsigned int seen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        if (seen >= csize) break;
+        if ((it & 255u) == 255u && globaltimer_ns() - t0 > 2000000000ull) asm volatile("trap;");
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");   // the team's generic-proxy stores, acquired above -> this thread's TMA reads
+      G_TRACE(6);
+      for (int kb = 0; kb < pre; ++kb) tma_load_2d(smem_u32(raw(kb)), &tmap_a, smem_u32(&raw_full[kb]), kb * TBK, m0);
+#pragma unroll 1
+      for (int kb = pre; kb < nkb; ++kb) {
+        const int s = kb % NRAW;
+        mbar_wait(smem_u32(&raw_empty[s]), ((kb / NRAW) - 1) & 1);
+        mbar_expect_tx(smem_u32(&raw_full[s]), Cfg::STAGE);
+        const uint32_t bar = smem_u32(&raw_full[s]), da = smem_u32(raw(kb));
+        tma_load_2d(da, &tmap_a, bar, kb * TBK, m0);
+        tma_load_2d(da + Cfg::A_BYTES, &tmap_b, bar, kb * TBK, n0);
+      }
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(smem_u32(&lo_full[kb % T_NLO]), (kb / T_NLO) & 1);
+      fence_async_smem();
+      tc_fence_after();
+      if (kb == 0) G_TRACE(8);
+      if (lane == 0) {
+        const uint32_t ah = smem_u32(raw(kb)), bh = ah + Cfg::A_BYTES, al = smem_u32(lo(kb)), bl = al + Cfg::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < TBK / 8; ++j) {
+          const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
+          umma_tf32(tmem_acc + BN, tma_desc<false>(al, j), tma_desc<false>(bh, j), idesc, first);  // cross terms
+          umma_tf32(tmem_acc + BN, tma_desc<false>(ah, j), tma_desc<false>(bl, j), idesc, 1u);
+          umma_tf32(tmem_acc, tma_desc<false>(ah, j), tma_desc<false>(bh, j), idesc, first);
+        }
+        umma_commit(smem_u32(&lo_empty[kb % T_NLO]));
+        umma_commit(smem_u32(&raw_empty[kb % NRAW]));
+        if (kb == nkb - 1) umma_commit(smem_u32(&acc_bar));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- phase 1: gather this CTA's share of the row tile ----------------
+    // Staging: every global load of the prologue is issued before the first shared-memory store (one memory round trip instead of
+    // one per table: the first version spent 5.7 us here), and only for the columns of THIS CTA's reduction blocks.
+    const int tid = threadIdx.x;
+    float* s_aff = reinterpret_cast<float*>(lo(0));                  // [2][G_KPAD]   (the lo stages are idle until phase 2)
+    float* s_S = s_aff + 2 * G_KPAD;                                // [BM][G_MAXQ]
+    float* s_T = s_S + BM * G_MAXQ;                                 // [G_MAXQ][G_KPAD]
+    const bool affine = g.fold.acc != nullptr || g.in_scale != nullptr;
+    const bool relu = g.relu != 0;
+    const int j = tid & 7;      // 16-byte chunk of the 128-byte block row
+    const int rb = tid >> 3;    // rows rb, rb + 32, rb + 64, rb + 96
+    // (a) this thread's four rows: in-degree and the first four neighbour ids, loop-invariant over the reduction blocks
+    int lo_[4], deg[4], src[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = m0 + rb + 32 * i;
+      const bool ok = gi < M;
+      lo_[i] = ok ? __ldg(g.rowptr + gi) : 0;
+      deg[i] = ok ? __ldg(g.rowptr + gi + 1) : -1;
+    }
+    // (b) tables: my own columns are those of blocks kb = crank, crank + csize, ...: column c is mine iff (c / 32) % csize == crank
+    const int my_blocks = (nkb - (int)crank + (int)csize - 1) / (int)csize;
+    const int my_cols = my_blocks * TBK;                       // <= 128 for K = 300 and three column tiles
+    // own column index (0 .. my_cols) -> global column
+    auto own_col = [&](int oc) { return ((oc / TBK) * (int)csize + (int)crank) * TBK + (oc % TBK); };
+    float bias_v = 0.f;
+    if (tid < BN) bias_v = (s_bias_on && n0 + tid < N) ? __ldg(ep.bias + n0 + tid) : 0.f;
+    float sv[5];   // BM * G_MAXQ = 1152 = 4.5 x 256
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int i = tid + u * NPRODUCER;
+      const int r = i / G_MAXQ, q = i - r * G_MAXQ;
+      sv[u] = (g.S && i < BM * G_MAXQ && m0 + r < M && q < g.Q) ? __ldg(g.S + (int64_t)(m0 + r) * g.Q + q) : 0.f;
+    }
+    float4 tv[5];  // G_MAXQ x my_cols / 4 <= 9 x 32 = 288 float4... per 32 columns; up to 4 blocks: 1152 = 4.5 x 256
+    const int tcnt = G_MAXQ * (my_cols / 4);
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int i = tid + u * NPRODUCER;
+      tv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g.S && i < tcnt) {
+        const int q = i / (my_cols / 4), c = own_col((i - q * (my_cols / 4)) * 4);
+        if (q < g.Q && c < K)
+          tv[u] = __ldg(reinterpret_cast<const float4*>(q < g.q_split ? g.T + (int64_t)q * K + c : g.T2 + (int64_t)(q - g.q_split) * K + c));
+      }
+    }
+    // (c) the affine of my columns (one column per thread: my_cols <= 128 < 256; wider shares loop)
+    for (int oc = tid; oc < my_cols; oc += NPRODUCER) {
+      const int c = own_col(oc);
+      if (c < K) {
+        if (g.fold.acc) bn_fold_column(g.fold, K, c, blockIdx.y == 0, s_aff[c], s_aff[G_KPAD + c]);   // row tile 0's team performs the module-state updates, each column once
+        else if (g.in_scale) { s_aff[c] = __ldg(g.in_scale + c); s_aff[G_KPAD + c] = __ldg(g.in_shift + c); }
+      }
+    }
+    // second round trip: neighbour ids (needs the row pointers)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (deg[i] >= 0) deg[i] -= lo_[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) src[i][k] = (k < deg[i]) ? __ldg(g.nbr + lo_[i] + k) : 0;
+    }
+    if (tid < BN) s_bias[tid] = bias_v;
+    if (g.S) {
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = tid + u * NPRODUCER;
+        if (i < BM * G_MAXQ) s_S[i] = sv[u];
+        if (i < tcnt) {
+          const int q = i / (my_cols / 4), c = own_col((i - q * (my_cols / 4)) * 4);
+          if (c < G_KPAD) *reinterpret_cast<float4*>(s_T + q * G_KPAD + c) = tv[u];
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
+    if (warp == 0) G_TRACE(3);
+#pragma unroll 1
+    for (int kb = (int)crank; kb < nkb; kb += (int)csize) {
+      const int col = kb * TBK + j * 4;
+      if (col >= K) continue;   // K % 4 == 0: whole chunks
+      // every row load of the block is issued before the first use; absent neighbours are predicated off inside the load
+      // instruction (with an `if (k < deg)` branch around the loads the compiler serialised them: 10 us per block)
+      float4 vs[4], vn[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gi = m0 + rb + 32 * i;
+        vs[i] = g_ldcg4(g.x + (int64_t)(deg[i] >= 0 ? gi : 0) * g.ldx + col, deg[i] >= 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vn[i][k] = g_ldcg4(g.x + (int64_t)src[i][k] * g.ldx + col, k < deg[i]);
+      }
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (affine) { sc = g_ld4(s_aff + col); sh = g_ld4(s_aff + G_KPAD + col); }
+      // the edge term does not depend on the gathered rows: it is computed while they are in flight
+      float4 ev[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // all Q bins unconditionally: fmaf(0, t, e) == e, so this equals k_aggregate_fwd's skip of the empty bins bit for bit
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.S) {
+          const float* sr = s_S + (rb + 32 * i) * G_MAXQ;
+#pragma unroll
+          for (int q = 0; q < G_MAXQ; ++q) {   // rows of s_S / s_T beyond Q are zero-filled
+            const float w = sr[q];
+            const float4 t = g_ld4(s_T + q * G_KPAD + col);
+            e.x = fmaf(w, t.x, e.x); e.y = fmaf(w, t.y, e.y); e.z = fmaf(w, t.z, e.z); e.w = fmaf(w, t.w, e.w);
+          }
+        }
+        ev[i] = e;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gi = m0 + rb + 32 * i;
+        if (deg[i] < 0) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float4 v = g_act(vn[i][k], sc, sh, affine, relu);
+          if (k >= deg[i]) v = make_float4(0.f, 0.f, 0.f, 0.f);   // acc + 0 == acc exactly (acc starts at +0 and never becomes -0)
+          g_add4(acc, v);
+        }
+        if (deg[i] > 4) {   // rare for molecules (a fifth bond): a plain serial loop, deliberately not unrolled (code size)
+#pragma unroll 1
+          for (int k = 4; k < deg[i]; ++k)
+            g_add4(acc, g_act(g_ldcg4(g.x + (int64_t)__ldg(g.nbr + lo_[i] + k) * g.ldx + col, true), sc, sh, affine, relu));
+        }
+        g_add4(acc, g_act(vs[i], sc, sh, affine, relu));   // self-loop last (chem/model.py:39)
+        if (g.S) g_add4(acc, ev[i]);
+        *reinterpret_cast<float4*>(g.aggr + (int64_t)gi * g.lda + col) = acc;
+      }
+    }
+    if (warp == 0) G_TRACE(4);
+    __threadfence();
+    if (warp == 0) G_TRACE(5);
+    asm volatile("fence.proxy.async;" ::: "memory");   // this thread's generic-proxy stores of aggr -> visible to the team's TMA reads
+    asm volatile("bar.sync 1, %0;" ::"n"(NPRODUCER) : "memory");
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(tile_ctr + blockIdx.y) : "memory");
+    if (warp == 0) G_TRACE(7);
+    // ---------------- phase 2: converters, exactly k_gemm_3xtf32_tma's ----------------
+    constexpr int V4 = Cfg::STAGE / 16;
+#pragma unroll 1
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(smem_u32(&raw_full[kb % NRAW]), (kb / NRAW) & 1);
+      if (kb >= T_NLO) mbar_wait(smem_u32(&lo_empty[kb % T_NLO]), ((kb / T_NLO) - 1) & 1);
+      const float4* src = reinterpret_cast<const float4*>(raw(kb));
+      float4* dst = reinterpret_cast<float4*>(lo(kb));
+#pragma unroll 4
+      for (int i = threadIdx.x; i < V4; i += NPRODUCER) {
+        const float4 v = src[i];
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        dst[i] = l;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&lo_full[kb % T_NLO]));
+    }
+  }
+  if (warp < NPRODUCER / 32) {
+    if (nkb > 0) mbar_wait(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    if (warp == 0) G_TRACE(9);
+    tc_epilogue_tma<BN>(smem, s_bias, s_bias_on, tmem_acc, nkb, m0, n0, M, N, &tmap_c, ep);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) G_TRACE(10);
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)tmem_cols<BN>()) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -694,6 +1031,41 @@ int dispatch_tma(int bn, const float* A, int64_t lda, const float* B, int64_t ld
   }
 }
 
+// Opt-in (PGNN_FUSED_GATHER=1 or pgnn_debug_set_fused_gather(1)).  Measured on the masking step (B = 256, one B200, same box):
+// fused 44.5 us per layer against 20.1 + 23 us for k_aggregate_fwd + GEMM1 -- the step is 1.154 ms fused, 1.120 ms unfused.  The
+// gather phase moves its 30 MB at the same ~3 TB/s of L2 gather bandwidth as the stand-alone kernel (11.8 us for a CTA's four
+// blocks), and what fusion removes (one launch, one drain) is paid back by the team hand-over (fence + counter + first A load:
+// 3.6 us) and the prologue's two dependent round trips (4.1 us) on the critical path of EVERY CTA; a 128-row tile cannot hide a
+// memory-bound phase under a tensor-bound one inside one CTA that holds 221 KB of shared memory (no co-resident partner).
+std::atomic<int> g_fused_gather{-1};
+bool fused_gather_enabled() {
+  int v = g_fused_gather.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("PGNN_FUSED_GATHER");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_fused_gather.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
+}
+
+template <int BN>
+int launch_gin_gather(const GinGather& g, const float* W, int64_t ldw, float* C, int64_t ldc, int M, int N, int K, const TcEpilogue& ep,
+                      unsigned int* tile_ctr, cudaStream_t st) {
+  const int nt = (int)ceil_div(N, BN), mt = (int)ceil_div(M, BM);
+  alignas(64) CUtensorMap ma, mb, mc;
+  if (!cached_map(&ma, g.aggr, false, M, K, g.lda, BM) || !cached_map(&mb, W, false, N, K, ldw, BN) || !cached_map_c(&mc, C, M, N, ldc, 1, 0))
+    return PGNN_EUNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    PGNN_CUDA(cudaFuncSetAttribute(k_gin_gather_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaCfg<BN, false>::SMEM));
+    configured = true;
+  }
+  dim3 grid((unsigned)nt, (unsigned)mt, 1u);   // x fastest: the CTAs of a team are adjacent in launch order
+  PGNN_CUDA(pgnn_launch(k_gin_gather_gemm<BN>, dim3(grid), dim3(T_NTHREADS), TmaCfg<BN, false>::SMEM, st, ma, mb, mc, M, N, K, ep, g, tile_ctr));
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+
 }  // namespace
 
 // C[M,N] = sum_k A(m,k) B(n,k) (+ epilogue) with TMA-staged operands; a_mn / b_mn select the operand major (see the top
@@ -709,8 +1081,39 @@ int pgnn_tma_gemm(bool a_mn, bool b_mn, int bn, const float* A, int64_t lda, con
   return PGNN_EUNSUPPORTED;
 }
 
+// aggr = gather(x) and z1[M,N] = relu?(aggr . W^T + bias) in one kernel (k_gin_gather_gemm; see GinGather).  PGNN_EUNSUPPORTED when the
+// shape / alignment does not fit (the caller then runs pgnn_internal_aggregate_fwd + the plain GEMM).
+int pgnn_tma_gin_gather_gemm(const float* x, int64_t ldx, const float* in_scale, const float* in_shift, const PgnnBnFold* fold, int in_relu,
+                             const int32_t* rowptr_t, const int32_t* nbr_t, const float* S, int Q, const float* T, const float* T2,
+                             int q_split, float* aggr, int64_t lda, const float* W, const float* bias, int relu, float* z1, int64_t ldz,
+                             int64_t M, int64_t N, int64_t K, unsigned int* tile_ctr, cudaStream_t st) {
+  // tile_ctr: ceil(M / 128) zeroed uint32 (arrival counters of the row-tile teams; consumed by this call)
+  if (!tile_ctr || !fused_gather_enabled() || !tma_store_enabled()) return PGNN_EUNSUPPORTED;
+  if (K % 4 || K > G_KPAD || ldx % 4 || !aggr || lda % 4 || ldz % 4 || (S && (Q < 1 || Q > G_MAXQ)) || M < 1) return PGNN_EUNSUPPORTED;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(x) || !al(W) || !al(z1) || (aggr && !al(aggr)) || (T && !al(T)) || (T2 && !al(T2))) return PGNN_EUNSUPPORTED;
+  GinGather g{};
+  g.x = x; g.ldx = ldx; g.in_scale = in_scale; g.in_shift = in_shift;
+  if (fold) g.fold = *fold;
+  g.relu = in_relu; g.rowptr = rowptr_t; g.nbr = nbr_t; g.S = S; g.Q = Q; g.T = T; g.T2 = T2 ? T2 : T; g.q_split = T2 ? q_split : Q;
+  g.aggr = aggr; g.lda = lda;
+  TcEpilogue ep{bias, relu, nullptr, 0, 0, PgnnGemmHooks{}};
+  if (N <= 112) return launch_gin_gather<112>(g, W, K, z1, ldz, (int)M, (int)N, (int)K, ep, tile_ctr, st);
+  return launch_gin_gather<208>(g, W, K, z1, ldz, (int)M, (int)N, (int)K, ep, tile_ctr, st);
+}
+
 extern "C" __attribute__((visibility("default"))) int pgnn_debug_tma_trace(unsigned long long* host16) {
   return cudaMemcpyFromSymbol(host16, g_tc_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
+}
+
+// development / tests: 1 = fused gather + GEMM1 kernel on the chem GIN encoder path, 0 = separate kernels, -1 = re-read PGNN_FUSED_GATHER
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_set_fused_gather(int on) {
+  g_fused_gather.store(on < 0 ? -1 : (on ? 1 : 0), std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int pgnn_debug_gather_trace(unsigned long long* host16) {
+  return cudaMemcpyFromSymbol(host16, g_gather_trace, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
 }
 
 #ifdef PGNN_TRACE_ALL

@@ -733,6 +733,18 @@ def _deliver_flat_grads(plan, ctx, run):
 
 
 
+def _release_ctx(ctx):
+    """Drop the encoder node's references to its ~200 MB workspace and inputs once the backward has been enqueued.  They are plain
+    ctx attributes (not save_for_backward tensors), so autograd does not free them with the graph's buffers: as long as the caller
+    keeps the loss tensor (e.g. to log it after the NEXT step has started), loss.grad_fn keeps this node and the node kept the
+    workspace, the next forward then needed a second one, and that cudaMalloc (40 ms, device-synchronising) was the stall seen at
+    step 1 of every end-to-end loop.  A second backward through the same graph is not supported by these ops anyway."""
+    ctx.ws = ctx.keep = ctx.ptrs = ctx.x = None
+    if hasattr(ctx, "ea"):
+        ctx.ea = None
+    ctx.released = True
+
+
 class _ChemGinEncoder(Function):
     @staticmethod
     def forward(ctx, plan, x, edge_index, edge_attr, training, *params):
@@ -776,6 +788,9 @@ class _ChemGinEncoder(Function):
     def backward(ctx, g):
         if not ctx.training:
             raise PgnnError("backward through the eval-mode encoder is not implemented (SURVEY.md section 3.3)")
+        if getattr(ctx, "released", False):
+            raise PgnnError("the whole-encoder op released its workspace after its first backward: a second backward through the same "
+                            "graph (retain_graph) is not supported; set model.fused = False for that")
         plan = ctx.plan
         N, E, L, D = ctx.dims
         g = _f32(g)
@@ -783,7 +798,9 @@ class _ChemGinEncoder(Function):
         def run(flat):
             check(lib.pgnn_chem_gin_backward(ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), N, E, L, D, _precision, _p(flat), _p(ctx.ws),
                                              ctx.wsb, _st()), "chem_gin_backward")
-        return _deliver_flat_grads(plan, ctx, run)
+        out = _deliver_flat_grads(plan, ctx, run)
+        _release_ctx(ctx)
+        return out
 
 
 def chem_gin_relu_masks(plan: ChemGinPlan, gnn):
@@ -891,6 +908,9 @@ class _ChemConvEncoder(Function):
     def backward(ctx, g):
         if not ctx.training:
             raise PgnnError("backward through the eval-mode encoder is not implemented (SURVEY.md section 3.3)")
+        if getattr(ctx, "released", False):
+            raise PgnnError("the whole-encoder op released its workspace after its first backward: a second backward through the same "
+                            "graph (retain_graph) is not supported; set model.fused = False for that")
         plan = ctx.plan
         N, E, L, D = ctx.dims
         g = _f32(g)
@@ -898,7 +918,9 @@ class _ChemConvEncoder(Function):
         def run(flat):
             check(lib.pgnn_chem_conv_backward(plan.conv, ctx.ptrs, _p(g), g.stride(0), _p(ctx.x), _p(ctx.ea), N, E, L, D, _precision,
                                               _p(flat), _p(ctx.ws), ctx.wsb, _st()), "chem_conv_backward")
-        return _deliver_flat_grads(plan, ctx, run)
+        out = _deliver_flat_grads(plan, ctx, run)
+        _release_ctx(ctx)
+        return out
 
 
 def chem_conv_encoder(plan: ChemConvPlan, x, edge_index, edge_attr, training: bool):

@@ -167,15 +167,23 @@ def test_batch_norm_train(M, C, relu):
     import copy
     bd = copy.deepcopy(bn).to(DEV)
     x = (rnd(M, C, seed=1) * 2 + 3).requires_grad_(True)  # mean >> 0 stresses the variance computation
-    y = bn(x)
-    y = torch.relu(y) if relu else y
+    pre = bn(x)
+    y = torch.relu(pre) if relu else pre
     R = rnd(M, C, seed=2)
     (y * R).sum().backward()
     xd = x.detach().to(DEV).requires_grad_(True)
     yd = ops.batch_norm(xd, bd, relu)
     (yd * R.to(DEV)).sum().backward()
     close(yd, y, 1e-4, 1e-4)
-    close(xd.grad, x.grad, 1e-4, 1e-3)
+    if relu:
+        # an element whose pre-activation is within rounding of zero may take the other ReLU branch on the GPU (the batch statistics
+        # are accumulated in a different order): its own gradient then differs by R, not by rounding.  Compare everything else.
+        edge = pre.detach().abs() <= 2e-6
+        assert int(edge.sum()) <= 8
+        g_dev = torch.where(edge, x.grad, xd.grad.cpu())
+        close(g_dev, x.grad, 1e-4 + 4e-4 * int(edge.any()), 1e-3)
+    else:
+        close(xd.grad, x.grad, 1e-4, 1e-3)
     close(bd.weight.grad, bn.weight.grad, 1e-4 * M ** 0.5, 1e-4)
     close(bd.bias.grad, bn.bias.grad, 1e-4 * M ** 0.5, 1e-4)
     close(bd.running_mean, bn.running_mean, 1e-5, 1e-5)
