@@ -25,6 +25,9 @@ REF_SRC = "/root/reference"
 REF_STAGED = os.path.join(HERE, "_ref")
 STANDIN = os.path.join(HERE, "pyg103_standin")
 FILES = ("model.py", "batch.py", "loader.py", "dataloader.py", "util.py")
+# shipped checkpoints behind tests/golden/pretrained.npz (tests/golden_util.PRETRAINED): staged, never committed
+WEIGHTS = ("chem/model_gin/masking.pth", "chem/model_architecture/gcn_contextpred.pth", "chem/model_architecture/gat_contextpred.pth",
+           "chem/model_architecture/graphsage_contextpred.pth", "bio/model_gin/masking.pth")
 _LOCAL_MODULES = ("model", "loader", "dataloader", "batch", "util", "splitters")
 
 
@@ -39,8 +42,14 @@ def stage(verbose=True):
             src = os.path.join(REF_SRC, domain, f)
             if os.path.exists(src):
                 shutil.copyfile(src, os.path.join(dst, f))
+    for f in WEIGHTS:
+        src, dst = os.path.join(REF_SRC, f), os.path.join(REF_STAGED, "weights", f)
+        if os.path.exists(src) and not (os.path.exists(dst) and os.path.getsize(dst) == os.path.getsize(src)):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
     with open(os.path.join(REF_STAGED, "PROVENANCE.txt"), "w") as fh:
-        fh.write("byte copies of /root/reference/{chem,bio}/{%s}; staged by oracle/reference_runner.py; git-ignored\n" % ",".join(FILES))
+        fh.write("byte copies of /root/reference/{chem,bio}/{%s} and, under weights/, of the checkpoints %s; staged by "
+                 "oracle/reference_runner.py; git-ignored\n" % (",".join(FILES), ", ".join(WEIGHTS)))
     if verbose:
         print("staged reference files under", REF_STAGED)
     return True

@@ -20,6 +20,36 @@ def golden_batch(domain):
     return syn.ppi_batch(c["graphs"], c["data_seed"], n_lo=40, n_hi=60, num_tasks=16)
 
 
+# Shipped checkpoints of the reference (SURVEY.md section 8(d) config 1 and section 8(c) "what does pin behaviour" (i)): goldens in
+# tests/golden/pretrained.npz (make_golden_pretrained.py); the files travel to the GPU box as git-ignored
+# oracle/_ref/weights/<domain>/<dir>/<file> (oracle/reference_runner.stage).
+PRETRAINED = {
+    "chem_gin": dict(domain="chem", type="gin", file="chem/model_gin/masking.pth", graphs=32, seed=1001),
+    "chem_gcn": dict(domain="chem", type="gcn", file="chem/model_architecture/gcn_contextpred.pth", graphs=32, seed=1002),
+    "chem_gat": dict(domain="chem", type="gat", file="chem/model_architecture/gat_contextpred.pth", graphs=8, seed=1003),
+    "chem_graphsage": dict(domain="chem", type="graphsage", file="chem/model_architecture/graphsage_contextpred.pth", graphs=8,
+                           seed=1004),
+    "bio_gin": dict(domain="bio", type="gin", file="bio/model_gin/masking.pth", graphs=2, seed=1005),
+}
+
+
+def pretrained_batch(name):
+    c = PRETRAINED[name]
+    if c["domain"] == "chem":
+        return syn.zinc_batch(c["graphs"], c["seed"])
+    return syn.ppi_batch(c["graphs"], c["seed"], n_lo=80, n_hi=120, num_tasks=16)
+
+
+def pretrained_state_dict(name):
+    """The checkpoint of PRETRAINED[name]: from /root/reference in the build container, from the staged copy on the GPU box."""
+    c = PRETRAINED[name]
+    for root in ("/root/reference", os.path.join(os.path.dirname(HERE), "oracle", "_ref", "weights")):
+        path = os.path.join(root, c["file"])
+        if os.path.isfile(path):
+            return torch.load(path, map_location="cpu", weights_only=True), path
+    return None, None
+
+
 def golden_params(domain, t):
     return O.make_params(domain, t, 5, 300, seed=CASES[domain]["param_seed"])
 

@@ -50,3 +50,27 @@ def test_cycle_rows_matches_reference_definition():
         arr = torch.arange(num) + shift
         arr[-shift:] = torch.arange(shift)
         assert torch.equal(arr, O.cycle_rows(num, shift))
+
+
+@pytest.mark.parametrize("name", sorted(__import__("golden_util").PRETRAINED))
+def test_oracle_matches_reference_with_shipped_checkpoint(name):
+    """eval-mode forward with the reference's shipped weights (chem GIN masking.pth at B = 32; the GCN
+    checkpoint reaches |x| ~ 190; GAT / GraphSAGE / bio GIN).  Golden = the reference's own model.py on the same checkpoint."""
+    import hashlib
+    import numpy as np
+    import os
+    from golden_util import HERE, PRETRAINED, pretrained_batch, pretrained_state_dict
+    torch.set_num_threads(1)
+    c = PRETRAINED[name]
+    G = np.load(os.path.join(HERE, "golden", "pretrained.npz"))
+    sd, path = pretrained_state_dict(name)
+    if sd is None:
+        pytest.skip("checkpoint not staged (run __graft_entry__.build() in the build container)")
+    assert bytes(G[name + ":sha256"]) == hashlib.sha256(open(path, "rb").read()).digest(), "staged checkpoint differs"
+    b = pretrained_batch(name)
+    assert input_checksum(b) == G[name + ":input_checksum"], "synthetic generator drifted from the golden inputs"
+    fwd = O.chem_gnn if c["domain"] == "chem" else O.bio_gnn
+    with torch.no_grad():
+        out = fwd(sd, b["x"], b["edge_index"], b["edge_attr"], 5, c["type"], False)
+    ref = torch.from_numpy(G[name + ":out_eval"])
+    assert bool(((out - ref).abs() <= 1e-4 + 1e-4 * ref.abs()).all()), float((out - ref).abs().max())
