@@ -355,6 +355,43 @@ PGNN_API int pgnn_collate_bio(const int64_t* node_ptr, const int64_t* edge_ptr, 
                               int64_t* node_off, int64_t* edge_off, float* x, int64_t* edge_index, float* edge_attr,
                               int64_t* batch, void* stream);
 
+/* ExtractSubstructureContextPair + BatchSubstructContext.from_data_list on the device (chem/util.py:55-151 through
+ * chem/loader.py:146-221, chem/batch.py:141-210; bio/util.py:123-205, bio/batch.py:196-265) for graphs held in HBM.
+ * Per selected graph i (root r_i = roots[i], graph-local; roots == NULL: r_i = splitmix64(seed, i) mod n_i, a uniform draw --
+ * the reference's random.sample cannot be matched bit for bit): d(v) = hop distance from r_i in the undirected graph of the
+ * even-indexed edge columns (pair p = columns 2p, 2p+1; pair_first[p] = 0 marks a pair whose endpoints already occurred and
+ * which networkx therefore ignores, chem/loader.py:173; every graph must hold an even number of columns);
+ *   whole_graph = 0 (chem): substructure = {d <= k}, context = {d <= l1} xor {d <= l2}, a cutoff <= 0 meaning {root};
+ *   whole_graph = 1 (bio):  substructure = the whole graph, context = {d > l1} (k, l2 ignored);
+ * overlap = substructure & context; a graph with an empty context is dropped from the batch (chem/batch.py:168).
+ * pgnn_extract_pairs runs the BFS and the scans: offsets [6][B+1] int64 receives the exclusive scans over the batch of
+ * (substructure nodes, substructure edge columns, context nodes, context edge columns, overlap entries, kept flag);
+ * offsets[q][B] are the totals the host reads back to size its views.  pgnn_extract_fill_{chem,bio} then write the batch:
+ * nodes renumbered ascending by original index, both directions of a kept pair adjacent ((i,j),(j,i), the attribute row of
+ * column 2p), edge_index compact [2, total], centre / overlap indices offset by their side's running node count,
+ * batch_overlapped_context = ordinal among the kept graphs.  Output buffers must hold the upper bounds: full_nodes rows and
+ * the selected graphs' full edge-column count.  full_nodes = sum of n_i (the host knows it from its copy of node_ptr).
+ * Integer work, bit-exact against oracle/step_io_oracle.extract_pairs_batch. */
+PGNN_API int64_t pgnn_extract_pairs_workspace_bytes(int64_t B, int64_t full_nodes);
+PGNN_API int pgnn_extract_pairs(const int64_t* node_ptr, const int64_t* edge_ptr, const int32_t* store_edge_index,
+                                int64_t store_num_edges, const uint8_t* pair_first, const int64_t* graph_ids, int64_t B,
+                                int64_t full_nodes, const int32_t* roots, int64_t seed, int k, int l1, int l2, int whole_graph,
+                                void* workspace, int64_t workspace_bytes, int64_t* offsets, void* stream);
+PGNN_API int pgnn_extract_fill_chem(const int64_t* node_ptr, const int64_t* edge_ptr, const uint8_t* store_x,
+                                    const int32_t* store_edge_index, int64_t store_num_edges, const uint8_t* store_edge_attr,
+                                    const uint8_t* pair_first, const int64_t* graph_ids, int64_t B, int64_t full_nodes,
+                                    const void* workspace, const int64_t* offsets, int64_t* x_substruct,
+                                    int64_t* edge_index_substruct, int64_t* edge_attr_substruct, int64_t* center_substruct_idx,
+                                    int64_t* x_context, int64_t* edge_index_context, int64_t* edge_attr_context,
+                                    int64_t* overlap_context_substruct_idx, int64_t* batch_overlapped_context,
+                                    int64_t* overlapped_context_size, void* stream);
+PGNN_API int pgnn_extract_fill_bio(const int64_t* node_ptr, const int64_t* edge_ptr, const int32_t* store_edge_index,
+                                   int64_t store_num_edges, const uint16_t* store_edge_bits, const uint8_t* pair_first,
+                                   const int64_t* graph_ids, int64_t B, int64_t full_nodes, const void* workspace,
+                                   const int64_t* offsets, float* x_context, int64_t* edge_index_context,
+                                   float* edge_attr_context, int64_t* overlap_context_substruct_idx,
+                                   int64_t* batch_overlapped_context, int64_t* overlapped_context_size, void* stream);
+
 /* Multi-tensor Adam: torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.decay).step()
  * (chem/pretrain_masking.py:134-136,72-74; chem/pretrain_contextpred.py:160-161,96-97) for every tensor in one launch.
  * `chunks` is a DEVICE array; each chunk is a contiguous run of at most a few thousand elements of one tensor

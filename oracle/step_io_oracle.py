@@ -115,3 +115,142 @@ def collate_bio(graphs, ids):
                 edge_attr=np.concatenate(eas, 0) if eas else np.zeros((0, 9), np.float32),
                 batch=np.concatenate(bs) if bs else np.zeros(0, np.int64),
                 node_off=np.array(node_off, dtype=np.int64), edge_off=np.array(edge_off, dtype=np.int64))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ExtractSubstructureContextPair (SURVEY.md 8(f) f4): restatement of chem/util.py:55-151 (+ chem/loader.py:146-221, the
+# networkx round trip it goes through) and bio/util.py:123-205, each followed by BatchSubstructContext.from_data_list
+# (chem/batch.py:141-210, bio/batch.py:196-265).
+#
+# What the reference computes per graph, root r:  d(v) = hop distance from r in the UNDIRECTED graph whose edges are the
+# even-indexed columns of edge_index (chem/loader.py:169: `for j in range(0, num_bonds, 2)`; a pair already present is
+# skipped, :173);  ball(c) = {v : d(v) <= c} with a negative cutoff (the constructor's 0 -> -1 quirk, chem/util.py:73-78)
+# giving {r};  substructure = ball(k);  context = ball(l1) symmetric-difference ball(l2);  overlap = context & substructure.
+# Both node sets are relabelled 0..m-1 and re-emitted through nx_to_graph_data_obj_simple: every kept undirected edge
+# becomes two adjacent columns (i,j),(j,i) with the same attribute row.  A graph whose context is empty is DROPPED from the
+# batch (chem/batch.py:168 "If there is no context, just skip!!").  bio: the substructure is the whole graph, the context is
+# everything outside ball(l1) and every context node is an overlap node (bio/util.py:176-199).
+#
+# Ordering: the reference numbers the nodes of a set in networkx's subgraph-view iteration order (graph order when the
+# set holds at least half of the nodes, CPython set order otherwise) and the edges in adjacency order; the overlap list is in
+# set order.  None of that is defined by the reference's source and no consumer depends on it (row gathers, mean pools and
+# permutation-equivariant encoders), so the order is DEFINED here: nodes ascending by original index, edges in the order of
+# their first column in the source, overlap ascending.  tests/test_oracle_vs_reference.py undoes the reference's
+# relabelling (it records `reset_idxes`' maps) and checks equality of node sets, per-node features, edge multisets,
+# centre and overlap; the device kernels are then bit-exact against this restatement.
+# ---------------------------------------------------------------------------------------------------------------------
+_INF = 1 << 30
+
+
+def first_pairs(ei):
+    """[e/2] bool: pair p = columns (2p, 2p+1); True where {u,v} was not seen in an earlier pair (chem/loader.py:173)."""
+    seen, out = set(), []
+    for p in range(ei.shape[1] // 2):
+        key = frozenset((int(ei[0, 2 * p]), int(ei[1, 2 * p])))
+        out.append(key not in seen)
+        seen.add(key)
+    return np.array(out, dtype=bool)
+
+
+def hop_distance(n, ei, root, first=None):
+    d = np.full(n, _INF, dtype=np.int64)
+    if n == 0:
+        return d
+    first = first_pairs(ei) if first is None else first
+    adj = [[] for _ in range(n)]
+    for p in np.nonzero(first)[0]:
+        u, v = int(ei[0, 2 * p]), int(ei[1, 2 * p])
+        adj[u].append(v)
+        adj[v].append(u)
+    d[root] = 0
+    frontier, level = [root], 0
+    while frontier:
+        level += 1
+        nxt = []
+        for u in frontier:
+            for v in adj[u]:
+                if d[v] == _INF:
+                    d[v] = level
+                    nxt.append(v)
+        frontier = nxt
+    return d
+
+
+def _ball(d, cutoff):
+    return d <= max(int(cutoff), 0)
+
+
+def _induced(ei, ea, first, member):
+    """Columns / attribute rows of the relabelled induced subgraph: kept pairs in source order, both directions adjacent."""
+    new = np.cumsum(member) - 1
+    cols, rows = [], []
+    for p in np.nonzero(first)[0]:
+        u, v = int(ei[0, 2 * p]), int(ei[1, 2 * p])
+        if member[u] and member[v]:
+            cols += [(new[u], new[v]), (new[v], new[u])]
+            rows += [ea[2 * p], ea[2 * p]]
+    ei2 = np.array(cols, dtype=np.int64).T.reshape(2, -1) if cols else np.zeros((2, 0), np.int64)
+    ea2 = np.array(rows) if rows else np.zeros((0,) + tuple(np.shape(ea)[1:]), dtype=np.asarray(ea).dtype)
+    return new, ei2, ea2
+
+
+def extract_pair(x, ei, ea, root, k, l1, l2, whole_graph=False):
+    """One graph -> dict (graph-local numbering) or None when the context is empty."""
+    n = len(x)
+    first = first_pairs(ei)
+    d = hop_distance(n, ei, root, first)
+    in_s = np.ones(n, dtype=bool) if whole_graph else _ball(d, k)
+    in_c = ~_ball(d, l1) if whole_graph else (_ball(d, l1) ^ _ball(d, l2))
+    if not in_c.any():
+        return None
+    new_s, ei_s, ea_s = _induced(ei, ea, first, in_s)
+    new_c, ei_c, ea_c = _induced(ei, ea, first, in_c)
+    if whole_graph and ea_c.shape[0]:
+        ea_c = ea_c.copy()
+        ea_c[:, 7:] = 0          # bio/loader.py:60-62: nx_to_graph_data_obj re-emits w1..w7 and zeros for self-loop / mask
+    return dict(x_substruct=np.asarray(x)[in_s], edge_index_substruct=ei_s, edge_attr_substruct=ea_s, center_substruct_idx=int(new_s[root]),
+                x_context=np.asarray(x)[in_c], edge_index_context=ei_c, edge_attr_context=ea_c,
+                overlap_context_substruct_idx=new_c[in_s & in_c].astype(np.int64), nodes_substruct=np.nonzero(in_s)[0], nodes_context=np.nonzero(in_c)[0])
+
+
+def extract_pairs_batch(graphs, ids, roots, k, l1, l2, whole_graph=False):
+    """graphs[g] = (x [n,F], edge_index [2,e] local, edge_attr [e,A]); roots[i] = graph-local root of batch slot i.
+    -> the BatchSubstructContext fields (chem/batch.py:150-205) + `kept` (batch slots that survived)."""
+    keys = ("x_substruct", "edge_index_substruct", "edge_attr_substruct", "x_context", "edge_index_context", "edge_attr_context")
+    acc = {k_: [] for k_ in keys}
+    center, overlap, seg, sizes, kept = [], [], [], [], []
+    cs = cc = 0
+    for slot, (g, r) in enumerate(zip(ids, roots)):
+        x, ei, ea = graphs[g]
+        p = extract_pair(np.asarray(x), np.asarray(ei), np.asarray(ea), int(r), k, l1, l2, whole_graph)
+        if p is None:
+            continue
+        i = len(kept)
+        kept.append(slot)
+        acc["x_substruct"].append(p["x_substruct"])
+        acc["edge_index_substruct"].append(p["edge_index_substruct"] + cs)
+        acc["edge_attr_substruct"].append(p["edge_attr_substruct"])
+        acc["x_context"].append(p["x_context"])
+        acc["edge_index_context"].append(p["edge_index_context"] + cc)
+        acc["edge_attr_context"].append(p["edge_attr_context"])
+        center.append(p["center_substruct_idx"] + cs)
+        overlap.append(p["overlap_context_substruct_idx"] + cc)
+        seg.append(np.full(len(p["overlap_context_substruct_idx"]), i, dtype=np.int64))
+        sizes.append(len(p["overlap_context_substruct_idx"]))
+        cs += len(p["x_substruct"])
+        cc += len(p["x_context"])
+    x0, a0 = np.asarray(graphs[0][0]), np.asarray(graphs[0][2])
+    empty = dict(x_substruct=np.zeros((0,) + x0.shape[1:], x0.dtype), x_context=np.zeros((0,) + x0.shape[1:], x0.dtype),
+                 edge_index_substruct=np.zeros((2, 0), np.int64), edge_index_context=np.zeros((2, 0), np.int64),
+                 edge_attr_substruct=np.zeros((0,) + a0.shape[1:], a0.dtype), edge_attr_context=np.zeros((0,) + a0.shape[1:], a0.dtype))
+    out = {k_: (np.concatenate(v, axis=1 if k_.startswith("edge_index") else 0) if v else empty[k_]) for k_, v in acc.items()}
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)
+    out.update(center_substruct_idx=np.array(center, dtype=np.int64), overlap_context_substruct_idx=cat(overlap),
+               batch_overlapped_context=cat(seg), overlapped_context_size=np.array(sizes, dtype=np.int64), kept=np.array(kept, dtype=np.int64))
+    return out
+
+
+def draw_roots(node_counts, seed):
+    """The root draw pgnn_extract_pairs defines when no roots are given: splitmix64(seed, batch slot) mod n (the reference
+    uses random.sample(range(n), 1), chem/util.py:100-101: a uniform draw, RNG parity impossible by construction)."""
+    return np.array([splitmix64(seed & _M64, i) % int(n) if n > 0 else 0 for i, n in enumerate(node_counts)], dtype=np.int64)

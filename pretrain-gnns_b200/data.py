@@ -16,6 +16,52 @@ import torch
 from ._cabi import check, lib
 
 
+def _pair_first(edge_ptr_host, edge_index):
+    """[Et/2] uint8: 1 where the bond pair (columns 2p, 2p+1) is the first of its graph with those endpoints.  The reference's
+    transforms go through networkx, which keeps one edge per unordered pair (chem/loader.py:173 `if not G.has_edge(...)`)."""
+    ep = np.asarray(edge_ptr_host, dtype=np.int64)
+    if (ep % 2).any():
+        raise ValueError("every graph must hold its bonds as adjacent (u,v),(v,u) column pairs (chem/loader.py:83-86)")
+    P = int(ep[-1]) // 2
+    if P == 0:
+        return np.zeros(0, np.uint8)
+    u, v = np.asarray(edge_index[0][0::2], dtype=np.int64), np.asarray(edge_index[1][0::2], dtype=np.int64)
+    lo, hi = np.minimum(u, v), np.maximum(u, v)
+    g = np.searchsorted(ep // 2, np.arange(P), side="right") - 1
+    M = int(hi.max()) + 1
+    key = (g * M + lo) * M + hi
+    _, first = np.unique(key, return_index=True)
+    out = np.zeros(P, np.uint8)
+    out[first] = 1
+    return out
+
+
+def _extract(store, ids, roots, seed, k, l1, l2, whole_graph):
+    """BFS + scans (pgnn_extract_pairs) -> (ids_dev, workspace, offsets [6,B+1] device, N_full, E_full)."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    if ids.size and (ids.min() < 0 or ids.max() >= store.num_graphs):
+        raise IndexError("graph id out of range")
+    dev, B = store.device, len(ids)
+    N = int((store.node_ptr_host[ids + 1] - store.node_ptr_host[ids]).sum())
+    E = int((store.edge_ptr_host[ids + 1] - store.edge_ptr_host[ids]).sum())
+    if store.pair_first is None:
+        store.pair_first = torch.from_numpy(_pair_first(store.edge_ptr_host, store.edge_index.cpu().numpy())).to(dev)
+    ids_dev = torch.from_numpy(ids).to(dev, non_blocking=True)
+    ws = torch.empty(int(check(lib.pgnn_extract_pairs_workspace_bytes(B, N), "pgnn_extract_pairs_workspace_bytes")), dtype=torch.uint8, device=dev)
+    offsets = torch.empty((6, B + 1), dtype=torch.int64, device=dev)
+    if roots is not None and not torch.is_tensor(roots):
+        roots = torch.from_numpy(np.ascontiguousarray(roots, dtype=np.int32)).to(dev, non_blocking=True)
+    if roots is not None:
+        roots = roots.to(torch.int32).contiguous()
+        if roots.numel() != B:
+            raise ValueError("one root per selected graph")
+    check(lib.pgnn_extract_pairs(store.node_ptr.data_ptr(), store.edge_ptr.data_ptr(), store.edge_index.data_ptr(), store.num_edges,
+                                 store.pair_first.data_ptr(), ids_dev.data_ptr(), B, N, None if roots is None else roots.data_ptr(),
+                                 int(seed) & ((1 << 63) - 1), int(k), int(l1), int(l2), int(whole_graph), ws.data_ptr(), ws.numel(),
+                                 offsets.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pgnn_extract_pairs")
+    return ids_dev, ws, offsets, N, E
+
+
 class MoleculeStore:
     """Compact CSR-of-graphs for chem molecules (value ranges: chem/loader.py:22-51; all fit a byte).
 
@@ -41,6 +87,7 @@ class MoleculeStore:
         self.x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8)).to(dev)
         self.edge_index = torch.from_numpy(np.ascontiguousarray(edge_index, dtype=np.int32)).to(dev)
         self.edge_attr = torch.from_numpy(np.ascontiguousarray(edge_attr, dtype=np.uint8)).to(dev)
+        self.pair_first = None    # built on first use by extract_pairs
 
     @classmethod
     def from_data_list(cls, data_list, device="cuda"):
@@ -81,6 +128,32 @@ class MoleculeStore:
                                     out.edge_off.data_ptr(), out.x.data_ptr(), out.edge_index.data_ptr(), out.edge_attr.data_ptr(),
                                     out.batch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pgnn_collate_chem")
         return out
+
+
+def extract_substruct_context_pairs(store, graph_ids_host, k, l1, l2, roots=None, seed=0):
+    """ExtractSubstructureContextPair(k, l1, l2) (chem/util.py:55-151; the script's defaults are k = num_layer, l1 = k - 1,
+    l2 = l1 + csize: chem/pretrain_contextpred.py:145-150) applied to the molecules `graph_ids_host` of a MoleculeStore and
+    collated as BatchSubstructContext.from_data_list does (chem/batch.py:141-210) -- on the device, three kernels, no
+    networkx.  `roots`: graph-local root atoms (host array or device tensor, one per graph); None draws them from `seed`
+    (a fresh value per step).  Returns the namespace SubstructContextStore.collate returns, plus `kept` = how many of the
+    selected molecules have a context (the reference silently drops the others, chem/batch.py:168).  One 48-byte read-back
+    sizes the views (the sizes are data dependent)."""
+    ids_dev, ws, offsets, N, E = _extract(store, graph_ids_host, roots, seed, k, l1, l2, 0)
+    B, dev = len(ids_dev), store.device
+    i64 = dict(dtype=torch.int64, device=dev)
+    xs, es, as_, cen = torch.empty((N, 2), **i64), torch.empty((2 * E,), **i64), torch.empty((E, 2), **i64), torch.empty((B,), **i64)
+    xc, ec, ac = torch.empty((N, 2), **i64), torch.empty((2 * E,), **i64), torch.empty((E, 2), **i64)
+    ov, seg, sizes = torch.empty((N,), **i64), torch.empty((N,), **i64), torch.empty((B,), **i64)
+    check(lib.pgnn_extract_fill_chem(store.node_ptr.data_ptr(), store.edge_ptr.data_ptr(), store.x.data_ptr(), store.edge_index.data_ptr(),
+                                     store.num_edges, store.edge_attr.data_ptr(), store.pair_first.data_ptr(), ids_dev.data_ptr(), B, N,
+                                     ws.data_ptr(), offsets.data_ptr(), xs.data_ptr(), es.data_ptr(), as_.data_ptr(), cen.data_ptr(), xc.data_ptr(),
+                                     ec.data_ptr(), ac.data_ptr(), ov.data_ptr(), seg.data_ptr(), sizes.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream), "pgnn_extract_fill_chem")
+    ns, e_s, nc, e_c, ko, kept = (int(v) for v in offsets[:, B].tolist())      # the one host read-back
+    return SimpleNamespace(x_substruct=xs[:ns], edge_index_substruct=es[:2 * e_s].view(2, e_s), edge_attr_substruct=as_[:e_s],
+                           center_substruct_idx=cen[:kept], x_context=xc[:nc], edge_index_context=ec[:2 * e_c].view(2, e_c),
+                           edge_attr_context=ac[:e_c], overlap_context_substruct_idx=ov[:ko], batch_overlapped_context=seg[:ko],
+                           overlapped_context_size=sizes[:kept], num_graphs=kept, kept=kept)
 
 
 def mask_atoms(batch, node_off_host, mask_rate=0.15, seed=0, num_atom_type=119):
@@ -172,6 +245,33 @@ class BioGraphStore:
         self.edge_index = torch.from_numpy(np.ascontiguousarray(ei)).to(dev)
         self.edge_bits = torch.from_numpy(bits.view(np.int16).copy()).to(dev)   # same 16 bits; torch has no uint16 arithmetic we need
         self.center = IndexLists([[int(c)] for c in center_idx], dev)
+        self.pair_first = None
+
+    def extract_context(self, graph_ids_host, l1):
+        """bio ExtractSubstructureContextPair(l1, center=True) + BatchSubstructContext.from_data_list (bio/util.py:123-205,
+        bio/batch.py:196-265) on the device: the substructure side is the ordinary collation of the whole ego graphs, the
+        context side holds the nodes further than l1 hops from the centre node, every one of them an overlap node.  Graphs
+        without a context are dropped by the reference; here that is reported (`kept`) and raised if it happens, because the
+        substructure side would have to be re-collated without them."""
+        ids = np.ascontiguousarray(graph_ids_host, dtype=np.int64)
+        out = self.collate(ids)
+        roots = self.center.values[torch.from_numpy(ids).to(self.device)]      # one centre per graph: list_ptr = arange
+        ids_dev, ws, offsets, N, E = _extract(self, ids, roots, 0, 0, l1, 0, 1)
+        B, dev = len(ids), self.device
+        i64, f32 = dict(dtype=torch.int64, device=dev), dict(dtype=torch.float32, device=dev)
+        xc, ec, ac = torch.empty((N, 1), **f32), torch.empty((2 * E,), **i64), torch.empty((E, 9), **f32)
+        ov, seg, sizes = torch.empty((N,), **i64), torch.empty((N,), **i64), torch.empty((B,), **i64)
+        check(lib.pgnn_extract_fill_bio(self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(), self.edge_index.data_ptr(), self.num_edges,
+                                        self.edge_bits.data_ptr(), self.pair_first.data_ptr(), ids_dev.data_ptr(), B, N, ws.data_ptr(),
+                                        offsets.data_ptr(), xc.data_ptr(), ec.data_ptr(), ac.data_ptr(), ov.data_ptr(), seg.data_ptr(),
+                                        sizes.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pgnn_extract_fill_bio")
+        _, _, nc, e_c, ko, kept = (int(v) for v in offsets[:, B].tolist())
+        if kept != B:
+            raise ValueError("%d of %d ego graphs have no node further than l1 = %d hops from their centre" % (B - kept, B, l1))
+        return SimpleNamespace(x_substruct=out.x, edge_index_substruct=out.edge_index, edge_attr_substruct=out.edge_attr,
+                               center_substruct_idx=out.center_node_idx, x_context=xc[:nc], edge_index_context=ec[:2 * e_c].view(2, e_c),
+                               edge_attr_context=ac[:e_c], overlap_context_substruct_idx=ov[:ko], batch_overlapped_context=seg[:ko],
+                               overlapped_context_size=sizes[:kept], num_graphs=kept, kept=kept)
 
     def collate(self, graph_ids_host):
         ids = np.ascontiguousarray(graph_ids_host, dtype=np.int64)

@@ -221,3 +221,87 @@ def test_substruct_context_and_bio_collate_device_vs_oracle():
         assert np.array_equal(getattr(o, k).cpu().numpy(), ref[k]), k
     cen, _, _, _ = SO.collate_lists(np.arange(7), np.array(centers), ids, add=ref["node_off"])
     assert np.array_equal(o.center_node_idx.cpu().numpy(), cen)
+
+
+_PAIR_KEYS = ("x_substruct", "edge_index_substruct", "edge_attr_substruct", "center_substruct_idx", "x_context", "edge_index_context",
+              "edge_attr_context", "overlap_context_substruct_idx", "batch_overlapped_context", "overlapped_context_size")
+
+
+@pytest.mark.parametrize("k,l1,l2", [(5, 4, 7), (2, 1, 3), (1, 0, 2), (0, 0, 1), (2, 5, 3)])
+def test_extract_substruct_context_pairs_device_vs_oracle(k, l1, l2):
+    """ExtractSubstructureContextPair + BatchSubstructContext on the device (pgnn_extract_pairs / pgnn_extract_fill_chem) against
+    oracle/step_io_oracle.extract_pairs_batch (itself checked against the reference's chem/util.py + chem/batch.py in
+    tests/test_oracle_vs_reference.py): bit-exact, for the script's default radii, small radii, the 0 -> -1 quirk and l1 > l2;
+    repeated graph ids, molecules with duplicate bonds, one-atom molecules (no context: dropped), given and drawn roots."""
+    G = 40
+    graphs = syn.split_graphs(syn.zinc_batch(G, 81))
+    graphs.append((graphs[1][0][:1], np.zeros((2, 0), np.int64), np.zeros((0, 2), np.int64)))   # a one-atom molecule
+    st = _store_from(graphs)
+    rng = np.random.default_rng(11)
+    ids = np.concatenate([rng.integers(0, G, size=70), [G, 3, G]])
+    rng.shuffle(ids)
+    n = np.array([len(graphs[g][0]) for g in ids])
+    roots = (rng.integers(0, 1 << 30, size=len(ids)) % n).astype(np.int64)
+    for given in (True, False):
+        if not given:
+            roots = SO.draw_roots(n, seed=4242)
+        out = data.extract_substruct_context_pairs(st, ids, k, l1, l2, roots=roots if given else None, seed=4242)
+        ref = SO.extract_pairs_batch(graphs, ids, roots, k, l1, l2)
+        assert out.kept == len(ref["kept"]) and out.kept <= len(ids) - 2
+        for key in _PAIR_KEYS:
+            mine = getattr(out, key).cpu().numpy()
+            assert mine.shape == ref[key].shape and np.array_equal(mine, ref[key]), (key, given)
+        assert out.edge_index_substruct.is_contiguous() and out.edge_index_context.is_contiguous()
+    assert not importlib.import_module("pretrain-gnns_b200.ops").device_errors()
+
+
+def test_extracted_pairs_feed_the_contextpred_step():
+    """The namespace extract_substruct_context_pairs returns is what ContextPredStep consumes (chem/pretrain_contextpred.py:50-97):
+    one training step on pairs extracted on the device runs and gives the loss the CPU oracle computes on the oracle's extraction."""
+    from oracle import steps_oracle as S
+    ts = importlib.import_module("pretrain-gnns_b200.train_steps")
+    graphs = syn.split_graphs(syn.zinc_batch(48, 83))
+    st = _store_from(graphs)
+    ids = np.arange(48)
+    roots = SO.draw_roots([len(g[0]) for g in graphs], seed=7)
+    out = data.extract_substruct_context_pairs(st, ids, 5, 4, 7, seed=7)
+    ref = SO.extract_pairs_batch(graphs, ids, roots, 5, 4, 7)
+    b = {key: torch.from_numpy(np.ascontiguousarray(ref[key])) for key in _PAIR_KEYS}
+    b["num_graphs"] = int(len(ref["kept"]))
+    step = ts.ContextPredStep(torch.device(DEV), batch_size=b["num_graphs"])
+    P = S.make_params("contextpred", 3)
+    step.load_state(P)
+    d = {key: getattr(out, key) for key in _PAIR_KEYS}
+    d["num_graphs"] = out.kept
+    loss = step(d)
+    l64 = S.grads_fp32_fp64(S.LOSSES["contextpred"], P, b)[3]
+    assert abs(float(loss) - float(l64)) <= 2e-6 * max(1.0, abs(float(l64))), (float(loss), float(l64))
+
+
+def test_extract_context_bio_device_vs_oracle():
+    """bio ExtractSubstructureContextPair(l1, center=True) on the device against the oracle (bio/util.py:123-205): context = nodes
+    further than l1 hops from the centre, every one an overlap node, self-loop / mask columns zeroed by the networkx round trip."""
+    pb = syn.ppi_batch(6, 29, n_lo=60, n_hi=90, pairs_per_node=2, num_tasks=4)
+    ptr = pb["ptr"].numpy()
+    ei, ea = pb["edge_index"].numpy(), pb["edge_attr"].numpy().copy()
+    ea[0:2, 8] = 1.0
+    owner = np.searchsorted(ptr, ei[0], side="right") - 1
+    eptr = np.searchsorted(owner, np.arange(len(ptr)))
+    graphs = [(int(ptr[g + 1] - ptr[g]), ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]]) for g in range(6)]
+    centers = [0, 3, 1, 0, 2, 5]
+    bs = data.BioGraphStore([g[0] for g in graphs], [g[1] for g in graphs], [g[2] for g in graphs], centers)
+    ids = np.array([5, 0, 0, 3, 2])
+    ograph = [(np.ones((g[0], 1), np.float32), g[1], g[2]) for g in graphs]
+    for l1 in (1, 2):
+        o = bs.extract_context(ids, l1)
+        ref = SO.extract_pairs_batch(ograph, ids, [centers[g] for g in ids], 0, l1, 0, whole_graph=True)
+        assert o.kept == len(ids)
+        for key in ("x_context", "edge_index_context", "edge_attr_context", "overlap_context_substruct_idx", "batch_overlapped_context",
+                    "overlapped_context_size"):
+            mine = getattr(o, key).cpu().numpy()
+            assert mine.shape == ref[key].shape and np.array_equal(mine, ref[key]), (key, l1)
+        full = SO.collate_bio(graphs, ids)
+        assert np.array_equal(o.edge_index_substruct.cpu().numpy(), full["edge_index"])
+        # whole-graph mode keeps every edge column of the substructure side only when no bond repeats; the centre is offset per graph
+        cen, _, _, _ = SO.collate_lists(np.arange(7), np.array(centers), ids, add=full["node_off"])
+        assert np.array_equal(o.center_substruct_idx.cpu().numpy(), cen)

@@ -242,3 +242,134 @@ def test_bio_collate_oracle_equals_reference():
         assert np.array_equal(mine[k], ref[k].numpy()), k
     cen, _, _, _ = SO.collate_lists(np.arange(6), np.array(centers), ids, add=mine["node_off"])
     assert np.array_equal(cen, ref.center_node_idx.numpy())
+
+
+def _canon_edges(ei, ea, nodes):
+    """Edge multiset in ORIGINAL node ids: sorted rows (u, v, attr...)."""
+    rows = [(int(nodes[int(ei[0, j])]), int(nodes[int(ei[1, j])])) + tuple(float(a) for a in np.asarray(ea[j]).ravel()) for j in range(ei.shape[1])]
+    return sorted(rows)
+
+
+def _ref_extract(util, transform, data, root):
+    """Run the reference's ExtractSubstructureContextPair and return its output together with the old->new node maps it
+    built (util.reset_idxes is a module-level function looked up at call time: wrap it to record the maps)."""
+    maps = []
+    orig = util.reset_idxes
+
+    def recording(G):
+        new_G, mapping = orig(G)
+        maps.append(dict(mapping))
+        return new_G, mapping
+
+    util.reset_idxes = recording
+    try:
+        out = transform(data, root_idx=root)
+    finally:
+        util.reset_idxes = orig
+    return out, maps
+
+
+@pytest.mark.parametrize("k,l1,l2", [(5, 4, 7), (2, 1, 3), (1, 0, 2), (0, 0, 1), (3, 3, 3), (2, 5, 3)])
+def test_extract_substruct_context_oracle_equals_reference_chem(k, l1, l2):
+    """oracle/step_io_oracle.extract_pair against the reference's own ExtractSubstructureContextPair.__call__(data, root_idx)
+    (chem/util.py:55-151) on molecules with duplicate bonds (the synthetic generator's extra pairs can repeat one), for the
+    script's default (k, l1, l2) = (5, 4, 7) (chem/pretrain_contextpred.py:145-150), small radii, the 0 -> -1 quirk, an
+    empty context (l1 == l2) and l1 > l2.  The reference's node numbering is undone through the maps it built."""
+    util = R.load("chem", "util")
+    from torch_geometric.data import Data
+    b = syn.zinc_batch(10, 61)
+    graphs = syn.split_graphs(b)
+    t = util.ExtractSubstructureContextPair(k, l1, l2)
+    rng = np.random.default_rng(7)
+    for x, ei, ea in graphs:
+        for root in {0, len(x) - 1, int(rng.integers(0, len(x)))}:
+            d = Data(x=torch.from_numpy(x.copy()), edge_index=torch.from_numpy(ei.copy()), edge_attr=torch.from_numpy(ea.copy()))
+            ref, maps = _ref_extract(util, t, d, root)
+            mine = SO.extract_pair(x, ei, ea, root, k, l1, l2)
+            if mine is None:
+                assert not hasattr(ref, "x_context") or ref.x_context is None
+                continue
+            ms, mc = maps[0], maps[1]
+            inv_s = {new: old for old, new in ms.items()}
+            inv_c = {new: old for old, new in mc.items()}
+            assert sorted(ms) == mine["nodes_substruct"].tolist() and sorted(mc) == mine["nodes_context"].tolist()
+            for new, old in inv_s.items():
+                assert np.array_equal(ref.x_substruct[new].numpy(), x[old])
+            for new, old in inv_c.items():
+                assert np.array_equal(ref.x_context[new].numpy(), x[old])
+            assert np.array_equal(mine["x_substruct"], x[mine["nodes_substruct"]]) and np.array_equal(mine["x_context"], x[mine["nodes_context"]])
+            ref_s = _canon_edges(ref.edge_index_substruct.numpy(), ref.edge_attr_substruct.numpy(), inv_s)
+            ref_c = _canon_edges(ref.edge_index_context.numpy(), ref.edge_attr_context.numpy(), inv_c)
+            assert ref_s == _canon_edges(mine["edge_index_substruct"], mine["edge_attr_substruct"], mine["nodes_substruct"])
+            assert ref_c == _canon_edges(mine["edge_index_context"], mine["edge_attr_context"], mine["nodes_context"])
+            assert inv_s[int(ref.center_substruct_idx)] == root == mine["nodes_substruct"][mine["center_substruct_idx"]]
+            ov_ref = sorted(inv_c[int(i)] for i in ref.overlap_context_substruct_idx) if hasattr(ref, "overlap_context_substruct_idx") and \
+                ref.overlap_context_substruct_idx is not None else []
+            assert ov_ref == mine["nodes_context"][mine["overlap_context_substruct_idx"]].tolist()
+
+
+def test_extract_pairs_batch_oracle_equals_reference_collation():
+    """extract_pairs_batch = the per-graph extraction followed by BatchSubstructContext.from_data_list (chem/batch.py:141-210),
+    including the reference's silent drop of pairs without a context.  The per-graph Data objects handed to the reference's
+    collator carry THIS oracle's (canonically ordered) fields, so the comparison is exact."""
+    batch_mod = R.load("chem", "batch")
+    from torch_geometric.data import Data
+    graphs = syn.split_graphs(syn.zinc_batch(8, 71))
+    ids = [3, 0, 7, 7, 2, 5]
+    roots = SO.draw_roots([len(graphs[g][0]) for g in ids], seed=99)
+    tiny = (graphs[1][0][:1], np.zeros((2, 0), np.int64), np.zeros((0, 2), np.int64))   # a one-atom molecule: no context -> dropped
+    graphs = graphs + [tiny]
+    ids, roots = ids[:3] + [8] + ids[3:], np.concatenate([roots[:3], [0], roots[3:]])
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    datas = []
+    for g, r in zip(ids, roots):
+        x, ei, ea = graphs[g]
+        p = SO.extract_pair(x, ei, ea, int(r), 2, 1, 3)
+        d = Data(x=T(x), edge_index=T(ei), edge_attr=T(ea))
+        if p is not None:
+            for k_ in ("x_substruct", "edge_index_substruct", "edge_attr_substruct", "x_context", "edge_index_context", "edge_attr_context",
+                       "overlap_context_substruct_idx"):
+                setattr(d, k_, T(p[k_]))
+            d.center_substruct_idx = torch.tensor([p["center_substruct_idx"]])
+        datas.append(d)
+    ref = batch_mod.BatchSubstructContext.from_data_list(datas)
+    mine = SO.extract_pairs_batch(graphs, ids, roots, 2, 1, 3)
+    assert mine["kept"].tolist() == [0, 1, 2, 4, 5, 6]
+    for k_ in ("x_substruct", "edge_index_substruct", "edge_attr_substruct", "center_substruct_idx", "x_context", "edge_index_context",
+               "edge_attr_context", "overlap_context_substruct_idx", "batch_overlapped_context", "overlapped_context_size"):
+        assert np.array_equal(mine[k_], ref[k_].numpy()), k_
+
+
+def test_extract_context_oracle_equals_reference_bio():
+    """bio/util.py:123-205 (substructure = the whole ego graph, context = everything further than l1 hops from the centre,
+    every context node an overlap node) on graphs without isolated nodes (bio/loader.py:119-142 builds the networkx graph
+    from the edges only: an isolated node would not exist in it and the reference raises a KeyError on the overlap map)."""
+    util = R.load("bio", "util")
+    from torch_geometric.data import Data
+    pb = syn.ppi_batch(3, 19, n_lo=30, n_hi=45, pairs_per_node=2, num_tasks=4)
+    ptr = pb["ptr"].numpy()
+    ei, ea = pb["edge_index"].numpy(), pb["edge_attr"].numpy()
+    owner = np.searchsorted(ptr, ei[0], side="right") - 1
+    eptr = np.searchsorted(owner, np.arange(len(ptr)))
+    for g in range(3):
+        n = int(ptr[g + 1] - ptr[g])
+        e, a = ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]].copy()
+        a[0:2, 8] = 1   # a masked pair (bio/util.py:100-102): the round trip through networkx drops the bit
+        if len(np.unique(e)) != n:
+            continue
+        for l1 in (1, 2):
+            t = util.ExtractSubstructureContextPair(l1, center=True)
+            d = Data(x=torch.ones(n, 1), edge_index=torch.from_numpy(e.copy()), edge_attr=torch.from_numpy(a.copy()), center_node_idx=torch.tensor([0]))
+            ref, maps = _ref_extract(util, t, d, None)
+            mine = SO.extract_pair(np.ones((n, 1), np.float32), e, a, 0, 0, l1, 0, whole_graph=True)
+            if mine is None:
+                assert not hasattr(ref, "x_context") or ref.x_context is None
+                continue
+            inv_c = {new: old for old, new in maps[0].items()}
+            assert sorted(maps[0]) == mine["nodes_context"].tolist()
+            assert tuple(ref.x_context.shape) == mine["x_context"].shape
+            # nx_to_graph_data_obj (bio/loader.py:76-116) re-emits w1..w7 and zeros for the self-loop / mask columns
+            assert _canon_edges(ref.edge_index_context.numpy(), ref.edge_attr_context.numpy(), inv_c) == \
+                _canon_edges(mine["edge_index_context"], mine["edge_attr_context"], mine["nodes_context"])
+            assert sorted(inv_c[int(i)] for i in ref.overlap_context_substruct_idx) == mine["nodes_context"][mine["overlap_context_substruct_idx"]].tolist()
+            assert np.array_equal(ref.edge_index_substruct.numpy(), e) and int(ref.center_substruct_idx) == 0
