@@ -335,7 +335,7 @@ PGNN_API int pgnn_collate_chem(const int64_t* node_ptr, const int64_t* edge_ptr,
  * node_off [B+1] as written by pgnn_collate_chem.  Outputs: mask_off [B+1] (exclusive scan of the sample sizes),
  * masked_atom_indices [M] (batch-global node ids, ascending inside a graph), mask_node_label [M,2]; M =
  * pgnn_mask_atoms_count(host copy of node_off, B, mask_rate).  Integer work, bit-exact against oracle/step_io_oracle.py.
- * Not built: mask_edge=True (chem/util.py:243-272; off by default in pretrain_masking.py). */
+ * mask_edge=True: follow with pgnn_mask_edges_chem. */
 PGNN_API int64_t pgnn_mask_atoms_count(const int64_t* node_off_host, int64_t B, double mask_rate);
 PGNN_API int pgnn_mask_atoms(int64_t* x, const int64_t* node_off, int64_t B, double mask_rate, int64_t mask_token, int64_t seed,
                              int64_t* mask_off, int64_t* masked_atom_indices, int64_t* mask_node_label, void* stream);
@@ -354,6 +354,26 @@ PGNN_API int pgnn_collate_bio(const int64_t* node_ptr, const int64_t* edge_ptr, 
                               int64_t store_num_edges, const uint16_t* store_edge_bits, const int64_t* graph_ids, int64_t B,
                               int64_t* node_off, int64_t* edge_off, float* x, int64_t* edge_index, float* edge_attr,
                               int64_t* batch, void* stream);
+
+/* The mask_edge=True half of MaskAtom (chem/util.py:243-272) on a collated batch whose atoms pgnn_mask_atoms has masked:
+ * per graph L = the edge columns with an endpoint in masked_atom_indices [M] (batch-global node ids), ascending;
+ * connected_edge_indices = L[::2] (+ the edge offset, chem/batch.py:41-42), mask_edge_label = edge_attr[L[::2]] (read before
+ * the overwrite), edge_attr[L] = [num_edge_type, 0] in place.  edge_index [2,E], edge_attr [E,2] int64; edge_off [B+1] as written
+ * by pgnn_collate_chem; conn_off [B+1] receives the exclusive scan of the per-graph list lengths (conn_off[B] = the total the
+ * host reads back); the two outputs must hold E/2 + B entries (rows).  Bit-exact against oracle/step_io_oracle.mask_edges_chem. */
+PGNN_API int64_t pgnn_mask_edges_chem_workspace_bytes(int64_t N, int64_t B);
+PGNN_API int pgnn_mask_edges_chem(const int64_t* edge_index, int64_t* edge_attr, const int64_t* edge_off, int64_t B, int64_t N,
+                                  int64_t E, const int64_t* masked_atom_indices, int64_t M, int64_t num_edge_type,
+                                  void* workspace, int64_t workspace_bytes, int64_t* conn_off, int64_t* connected_edge_indices,
+                                  int64_t* mask_edge_label, void* stream);
+/* MaskEdge (bio/util.py:46-104) on a batch collated by pgnn_collate_bio: per graph int(e/2 * mask_rate + 1) distinct bond pairs
+ * (uniform k-subset: the k smallest splitmix64(seed, column id) keys), masked_edge_idx [M] = their first columns (ascending, edge
+ * offset included: bio/batch.py:95-96), mask_edge_label [M,9] = their attribute rows, then both directions of each pair set to
+ * [0,0,0,0,0,0,0,0,1] in place.  M = pgnn_mask_edges_bio_count(host copy of edge_off, B, mask_rate); mask_off [B+1] receives
+ * the exclusive scan of the sample sizes.  Bit-exact against oracle/step_io_oracle.mask_edges_bio. */
+PGNN_API int64_t pgnn_mask_edges_bio_count(const int64_t* edge_off_host, int64_t B, double mask_rate);
+PGNN_API int pgnn_mask_edges_bio(float* edge_attr, const int64_t* edge_off, int64_t B, double mask_rate, int64_t seed,
+                                 int64_t* mask_off, int64_t* masked_edge_idx, float* mask_edge_label, void* stream);
 
 /* ExtractSubstructureContextPair + BatchSubstructContext.from_data_list on the device (chem/util.py:55-151 through
  * chem/loader.py:146-221, chem/batch.py:141-210; bio/util.py:123-205, bio/batch.py:196-265) for graphs held in HBM.

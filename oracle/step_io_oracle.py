@@ -86,6 +86,54 @@ def mask_atoms(x, node_off, rate, seed, mask_token=119):
     return x, idx, labels, np.array(off, dtype=np.int64)
 
 
+def mask_edges_chem(edge_index, edge_attr, edge_off, masked_atom_indices, num_edge_type=5):
+    """The mask_edge=True half of MaskAtom.__call__ (chem/util.py:243-272) graph by graph + BatchMasking's edge offset
+    (chem/batch.py:41-42), on the collated batch.  -> (edge_attr_masked, connected_edge_indices, mask_edge_label, conn_off)"""
+    ei = np.asarray(edge_index)
+    ea = np.array(edge_attr, dtype=np.int64, copy=True)
+    masked = set(int(i) for i in masked_atom_indices)
+    conn, labels, off = [], [], [0]
+    for g in range(len(edge_off) - 1):
+        L = [j for j in range(int(edge_off[g]), int(edge_off[g + 1])) if int(ei[0, j]) in masked or int(ei[1, j]) in masked]   # :246-251
+        sel = L[::2]                                                                                                                # :257, :268
+        labels += [ea[j].copy() for j in sel]
+        conn += sel
+        for j in L:
+            ea[j] = (num_edge_type, 0)                                                                                              # :263-265
+        off.append(len(conn))
+    lab = np.array(labels, dtype=np.int64).reshape(-1, 2)
+    return ea, np.array(conn, dtype=np.int64), lab, np.array(off, dtype=np.int64)
+
+
+def mask_edge_choice_bio(edge_off, rate, seed):
+    """Per graph: the int(e/2 * rate + 1) bond pairs with the smallest keys splitmix64(seed, column id of the pair's first
+    direction), ties by index, ascending; graph-LOCAL pair numbers (csrc/mask_edges.cu defines this draw)."""
+    out = []
+    for g in range(len(edge_off) - 1):
+        e0, m = int(edge_off[g]), int(edge_off[g + 1] - edge_off[g]) // 2
+        k = min(int(m * rate + 1), m) if m > 0 else 0            # bio/util.py:78-80
+        order = sorted(range(m), key=lambda i: (splitmix64(seed & _M64, e0 + 2 * i), i))
+        out.append(sorted(order[:k]))
+    return out
+
+
+def mask_edges_bio(edge_attr, edge_off, rate, seed):
+    """MaskEdge.__call__(data, masked_edge_indices=[2 i ...]) graph by graph + the edge offset of bio/batch.py:95-96.
+    -> (edge_attr_masked, masked_edge_idx, mask_edge_label, mask_off)"""
+    ea = np.array(edge_attr, dtype=np.float32, copy=True)
+    idx, off = [], [0]
+    for g, local in enumerate(mask_edge_choice_bio(edge_off, rate, seed)):
+        idx += [int(edge_off[g]) + 2 * i for i in local]
+        off.append(len(idx))
+    idx = np.array(idx, dtype=np.int64)
+    labels = ea[idx].copy() if len(idx) else np.zeros((0, 9), np.float32)
+    mask = np.array([0, 0, 0, 0, 0, 0, 0, 0, 1], dtype=np.float32)       # bio/util.py:98-102
+    for j in idx:
+        ea[j] = mask
+        ea[j + 1] = mask
+    return ea, idx, labels, np.array(off, dtype=np.int64)
+
+
 def collate_lists(list_ptr, values, ids, add=None):
     """Ragged per-graph index lists of a batch, each entry offset by `add[i]` -> (out, seg, sizes, list_off)."""
     out, seg, sizes, off = [], [], [], [0]

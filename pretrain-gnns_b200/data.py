@@ -156,6 +156,43 @@ def extract_substruct_context_pairs(store, graph_ids_host, k, l1, l2, roots=None
                            overlapped_context_size=sizes[:kept], num_graphs=kept, kept=kept)
 
 
+def mask_edges_bio(batch, edge_off_host, mask_rate=0.15, seed=0):
+    """MaskEdge (bio/util.py:46-104) on a batch collated by BioGraphStore.collate, on the device: adds `masked_edge_idx` [M],
+    `mask_edge_label` [M,9], `mask_edge_off` [B+1] and overwrites both directions of the chosen bond pairs in `batch.edge_attr`
+    with the mask vector.  `edge_off_host`: host copy of batch.edge_off (np.int64 [B+1])."""
+    import ctypes
+    off = np.ascontiguousarray(edge_off_host, dtype=np.int64)
+    B = len(off) - 1
+    M = int(check(lib.pgnn_mask_edges_bio_count(off.ctypes.data_as(ctypes.c_void_p), B, float(mask_rate)), "pgnn_mask_edges_bio_count"))
+    dev = batch.edge_attr.device
+    batch.masked_edge_idx = torch.empty((M,), dtype=torch.int64, device=dev)
+    batch.mask_edge_label = torch.empty((M, 9), dtype=torch.float32, device=dev)
+    batch.mask_edge_off = torch.empty((B + 1,), dtype=torch.int64, device=dev)
+    check(lib.pgnn_mask_edges_bio(batch.edge_attr.data_ptr(), batch.edge_off.data_ptr(), B, float(mask_rate), int(seed) & ((1 << 63) - 1),
+                                  batch.mask_edge_off.data_ptr(), batch.masked_edge_idx.data_ptr(), batch.mask_edge_label.data_ptr(),
+                                  torch.cuda.current_stream(dev).cuda_stream), "pgnn_mask_edges_bio")
+    return batch
+
+
+def mask_edges_chem(batch, num_edge_type=5):
+    """The mask_edge=True half of MaskAtom (chem/util.py:243-272) on a batch that mask_atoms has processed: adds
+    `connected_edge_indices` [Mc], `mask_edge_label` [Mc,2] and overwrites the attribute rows of every bond touching a masked
+    atom with [num_edge_type, 0].  The list length is data dependent: one 8-byte read-back narrows the views."""
+    dev = batch.x.device
+    N, E, B = int(batch.x.shape[0]), int(batch.edge_index.shape[1]), int(batch.node_off.shape[0]) - 1
+    M = int(batch.masked_atom_indices.shape[0])
+    ws = torch.empty(int(check(lib.pgnn_mask_edges_chem_workspace_bytes(N, B), "pgnn_mask_edges_chem_workspace_bytes")), dtype=torch.uint8, device=dev)
+    cap = E // 2 + B
+    conn, labels = torch.empty((cap,), dtype=torch.int64, device=dev), torch.empty((cap, 2), dtype=torch.int64, device=dev)
+    conn_off = torch.empty((B + 1,), dtype=torch.int64, device=dev)
+    check(lib.pgnn_mask_edges_chem(batch.edge_index.data_ptr(), batch.edge_attr.data_ptr(), batch.edge_off.data_ptr(), B, N, E,
+                                   batch.masked_atom_indices.data_ptr(), M, int(num_edge_type), ws.data_ptr(), ws.numel(), conn_off.data_ptr(),
+                                   conn.data_ptr(), labels.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "pgnn_mask_edges_chem")
+    total = int(conn_off[B])
+    batch.connected_edge_indices, batch.mask_edge_label, batch.connected_edge_off = conn[:total], labels[:total], conn_off
+    return batch
+
+
 def mask_atoms(batch, node_off_host, mask_rate=0.15, seed=0, num_atom_type=119):
     """MaskAtom (chem/util.py:189-241, mask_edge=False) on a batch collated by MoleculeStore.collate, on the device: adds
     `masked_atom_indices` [M], `mask_node_label` [M,2], `mask_off` [B+1] to `batch` and overwrites the masked rows of

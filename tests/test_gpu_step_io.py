@@ -305,3 +305,53 @@ def test_extract_context_bio_device_vs_oracle():
         # whole-graph mode keeps every edge column of the substructure side only when no bond repeats; the centre is offset per graph
         cen, _, _, _ = SO.collate_lists(np.arange(7), np.array(centers), ids, add=full["node_off"])
         assert np.array_equal(o.center_substruct_idx.cpu().numpy(), cen)
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_mask_edges_chem_device_vs_oracle(paired):
+    """MaskAtom(mask_edge=True) on the device (pgnn_mask_atoms + pgnn_mask_edges_chem) against the oracle (itself equal to the
+    reference's MaskAtom + BatchMasking): bit-exact; also on a batch with one direction of each bond deleted, where L[::2] no longer
+    means "one column per bond" and only the literal rule gives the reference's answer."""
+    st, graphs, _ = _store(60, 17)
+    rng = np.random.default_rng(2)
+    ids = rng.integers(0, 60, size=90)
+    b = st.collate(ids)
+    if not paired:
+        keep = torch.from_numpy(np.sort(rng.choice(b.edge_index.shape[1], size=b.edge_index.shape[1] * 2 // 3, replace=False))).to(DEV)
+        cnt = torch.zeros(len(ids) + 1, dtype=torch.int64, device=DEV)
+        owner = torch.searchsorted(b.edge_off, keep, right=True) - 1
+        cnt[1:] = torch.bincount(owner, minlength=len(ids))
+        b.edge_index, b.edge_attr, b.edge_off = b.edge_index[:, keep].contiguous(), b.edge_attr[keep].contiguous(), torch.cumsum(cnt, 0)
+    ei0, ea0, eoff = b.edge_index.cpu().numpy(), b.edge_attr.cpu().numpy().copy(), b.edge_off.cpu().numpy()
+    x0 = b.x.cpu().numpy().copy()
+    data.mask_atoms(b, st.node_offsets_host(ids), 0.15, seed=99)
+    data.mask_edges_chem(b, num_edge_type=5)
+    _, idx, _, _ = SO.mask_atoms(x0, st.node_offsets_host(ids), 0.15, seed=99)
+    ea2, conn, lab, off = SO.mask_edges_chem(ei0, ea0, eoff, idx)
+    assert np.array_equal(b.edge_attr.cpu().numpy(), ea2)
+    assert np.array_equal(b.connected_edge_indices.cpu().numpy(), conn) and np.array_equal(b.mask_edge_label.cpu().numpy(), lab)
+    assert np.array_equal(b.connected_edge_off.cpu().numpy(), off) and len(conn) > 0
+
+
+def test_mask_edges_bio_device_vs_oracle():
+    """MaskEdge on the device (pgnn_mask_edges_bio) against the oracle (equal to the reference's MaskEdge + bio BatchMasking):
+    bit-exact, incl. a graph larger than the kernel's shared-memory key cache (4096 pairs) and a graph without edges."""
+    pb = syn.ppi_batch(4, 37, n_lo=60, n_hi=90, pairs_per_node=3, num_tasks=4)
+    big = syn.ppi_batch(1, 38, n_lo=900, n_hi=900, pairs_per_node=5, num_tasks=4)
+    graphs = []
+    for src in (pb, big):
+        ptr = src["ptr"].numpy()
+        ei, ea = src["edge_index"].numpy(), src["edge_attr"].numpy()
+        owner = np.searchsorted(ptr, ei[0], side="right") - 1
+        eptr = np.searchsorted(owner, np.arange(len(ptr)))
+        graphs += [(int(ptr[g + 1] - ptr[g]), ei[:, eptr[g]:eptr[g + 1]] - ptr[g], ea[eptr[g]:eptr[g + 1]]) for g in range(len(ptr) - 1)]
+    graphs.append((3, np.zeros((2, 0), np.int64), np.zeros((0, 9), np.float32)))
+    bs = data.BioGraphStore([g[0] for g in graphs], [g[1] for g in graphs], [g[2] for g in graphs], [0] * len(graphs))
+    ids = np.array([4, 0, 5, 2, 2])
+    o = bs.collate(ids)
+    ea0, eoff = o.edge_attr.cpu().numpy().copy(), o.edge_off.cpu().numpy()
+    assert (eoff[1] - eoff[0]) // 2 > 4096
+    data.mask_edges_bio(o, eoff, 0.15, seed=5)
+    ea2, idx, lab, off = SO.mask_edges_bio(ea0, eoff, 0.15, seed=5)
+    assert np.array_equal(o.edge_attr.cpu().numpy(), ea2) and np.array_equal(o.masked_edge_idx.cpu().numpy(), idx)
+    assert np.array_equal(o.mask_edge_label.cpu().numpy(), lab) and np.array_equal(o.mask_edge_off.cpu().numpy(), off)

@@ -373,3 +373,51 @@ def test_extract_context_oracle_equals_reference_bio():
                 _canon_edges(mine["edge_index_context"], mine["edge_attr_context"], mine["nodes_context"])
             assert sorted(inv_c[int(i)] for i in ref.overlap_context_substruct_idx) == mine["nodes_context"][mine["overlap_context_substruct_idx"]].tolist()
             assert np.array_equal(ref.edge_index_substruct.numpy(), e) and int(ref.center_substruct_idx) == 0
+
+
+def test_mask_edges_chem_oracle_equals_reference_maskatom_mask_edge():
+    """oracle mask_edges_chem against the reference's MaskAtom(mask_edge=True).__call__(data, masked_atom_indices=choice)
+    (chem/util.py:243-272) followed by BatchMasking.from_data_list (chem/batch.py:17-52: connected_edge_indices + cumsum_edge)."""
+    util = R.load("chem", "util")
+    batch_mod = R.load("chem", "batch")
+    from torch_geometric.data import Data
+    b = syn.zinc_batch(9, 43)
+    graphs = syn.split_graphs(b)
+    node_off = b["ptr"].numpy()
+    choice = SO.mask_atom_choice(node_off, 0.15, seed=777)
+    t = util.MaskAtom(num_atom_type=119, num_edge_type=5, mask_rate=0.15, mask_edge=True)
+    datas = []
+    for (x, ei, ea), local in zip(graphs, choice):
+        d = Data(x=torch.from_numpy(x.copy()), edge_index=torch.from_numpy(ei.copy()), edge_attr=torch.from_numpy(ea.copy()))
+        datas.append(t(d, masked_atom_indices=list(local)))
+    ref = batch_mod.BatchMasking.from_data_list(datas)
+    x2, idx, _, _ = SO.mask_atoms(b["x"].numpy(), node_off, 0.15, seed=777)
+    edge_off = np.concatenate([[0], np.cumsum([g[1].shape[1] for g in graphs])])
+    ea2, conn, lab, off = SO.mask_edges_chem(b["edge_index"].numpy(), b["edge_attr"].numpy(), edge_off, idx)
+    assert np.array_equal(ea2, ref.edge_attr.numpy()) and np.array_equal(conn, ref.connected_edge_indices.numpy())
+    assert np.array_equal(lab, ref.mask_edge_label.numpy()) and off[-1] == len(conn) and len(conn) > 0
+
+
+def test_mask_edges_bio_oracle_equals_reference_maskedge():
+    """oracle mask_edges_bio against the reference's MaskEdge.__call__(data, masked_edge_indices=[2 i ...]) (bio/util.py:46-104)
+    followed by bio BatchMasking.from_data_list (bio/batch.py:71-105: masked_edge_idx + cumsum_edge)."""
+    util = R.load("bio", "util")
+    batch_mod = R.load("bio", "batch")
+    from torch_geometric.data import Data
+    pb = syn.ppi_batch(4, 23, n_lo=20, n_hi=35, pairs_per_node=3, num_tasks=4)
+    ptr = pb["ptr"].numpy()
+    ei, ea = pb["edge_index"].numpy(), pb["edge_attr"].numpy()
+    owner = np.searchsorted(ptr, ei[0], side="right") - 1
+    eptr = np.searchsorted(owner, np.arange(len(ptr)))
+    choice = SO.mask_edge_choice_bio(eptr, 0.15, seed=31)
+    assert [len(c) for c in choice] == [int((eptr[g + 1] - eptr[g]) // 2 * 0.15 + 1) for g in range(4)]
+    t = util.MaskEdge(mask_rate=0.15)
+    datas = []
+    for g in range(4):
+        n = int(ptr[g + 1] - ptr[g])
+        d = Data(x=torch.ones(n, 1), edge_index=torch.from_numpy(ei[:, eptr[g]:eptr[g + 1]] - ptr[g]), edge_attr=torch.from_numpy(ea[eptr[g]:eptr[g + 1]].copy()))
+        datas.append(t(d, masked_edge_indices=[2 * i for i in choice[g]]))
+    ref = batch_mod.BatchMasking.from_data_list(datas)
+    ea2, idx, lab, off = SO.mask_edges_bio(ea, eptr, 0.15, seed=31)
+    assert np.array_equal(ea2, ref.edge_attr.numpy()) and np.array_equal(idx, ref.masked_edge_idx.numpy())
+    assert np.array_equal(lab, ref.mask_edge_label.numpy()) and off[-1] == len(idx)
