@@ -9,6 +9,8 @@
 // in L2 after the first touch; see DESIGN.md for the roofline discussion.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -222,6 +224,77 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
   }
 }
 
+// float4 variant of k_edge_table_bwd: a lane owns FOUR adjacent columns (512-byte warp loads: a quarter of the load instructions
+// per byte) and the CTA's S rows are staged in shared memory once (coalesced) instead of Q broadcast loads per row and thread --
+// the scalar kernel issues 1 + Q load instructions per 128 useful bytes and is instruction-bound (59 us for 38 MB at N = 32 k).
+// 8 row-lanes x 32 column-lanes; the row-lanes are folded through shared memory eight table rows at a time.
+// Up to kTblJobs reductions over the same n rows in ONE launch (blockIdx.z): the GAT backward needs four per layer (two heads x
+// {message table, attention vector}), each a ~6 us kernel on a molecule batch.
+constexpr int kTblJobs = 4;
+struct TblJob {
+  const float* S;
+  const float* g;
+  float *gT, *gT2;
+  int64_t ldg, g_off, ldt;
+  int Q, q_split;
+};
+struct TblJobs { TblJob j[kTblJobs]; };
+
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+k_edge_table_bwd_v4(const __grid_constant__ TblJobs jobs, int64_t n, int C4) {
+  pdl_prologue();
+  const TblJob& job = jobs.j[blockIdx.z];
+  const float* __restrict__ S = job.S;
+  const float* __restrict__ g = job.g;
+  float* __restrict__ gT = job.gT;
+  float* __restrict__ gT2 = job.gT2;
+  const int64_t ldg = job.ldg, g_off = job.g_off, ldt = job.ldt;
+  const int Q = job.Q, q_split = job.q_split;
+  __shared__ float sS[ROWS * kMaxQ];
+  __shared__ float4 red[8][8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c4 = blockIdx.y * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.x * ROWS;
+  const int rows = (int)((r0 + ROWS < n) ? ROWS : n - r0);
+  for (int i = threadIdx.x; i < rows * Q; i += 256) sS[i] = S[r0 * Q + i];
+  __syncthreads();
+  float4 acc[kMaxQ];
+#pragma unroll
+  for (int q = 0; q < kMaxQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < C4) {
+    const float* gp = g + g_off + 4 * c4;
+#pragma unroll 4
+    for (int r = w; r < rows; r += 8) {
+      const float4 v = ld4(gp + (r0 + r) * ldg);
+      const float* s = sS + r * Q;
+#pragma unroll
+      for (int q = 0; q < kMaxQ; ++q)
+        if (q < Q) axpy4(acc[q], s[q], v);
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < kMaxQ / 8; ++pass) {
+    if (pass * 8 < Q) {            // uniform across the CTA
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) red[w][q][lane] = acc[pass * 8 + q];
+      __syncthreads();
+      const int q = pass * 8 + w;  // warp w folds table row pass * 8 + w
+      if (q < Q && c4 < C4) {
+        float4 t = red[0][w][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) add4(t, red[k][w][lane]);
+        float* dst = (q < q_split ? gT + (int64_t)q * ldt : gT2 + (int64_t)(q - q_split) * ldt) + 4 * c4;
+        atomicAdd(dst, t.x);
+        atomicAdd(dst + 1, t.y);
+        atomicAdd(dst + 2, t.z);
+        atomicAdd(dst + 3, t.w);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_chem_embed_fwd(const int64_t* __restrict__ x, const float* __restrict__ t1, const float* __restrict__ t2, int64_t n,
                  int C4, int rows1, int rows2, float* __restrict__ out, int64_t ldo, unsigned int* __restrict__ err) {
@@ -320,12 +393,48 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+namespace {
+bool table_v4_enabled() {
+  static const bool on = !(getenv("PGNN_TABLE_V4") && getenv("PGNN_TABLE_V4")[0] == '0');
+  return on;
+}
+int launch_table_v4(const TblJobs& jobs, int count, int64_t n, int C, cudaStream_t st) {
+  const int rows = n >= 16384 ? kTblRowsLarge : kTblRowsSmall;
+  dim3 grid4((unsigned)ceil_div(n, rows), (unsigned)ceil_div(C / 4, 32), (unsigned)count);
+  if (rows == kTblRowsLarge)
+    PGNN_CUDA(pgnn_launch(k_edge_table_bwd_v4<kTblRowsLarge>, dim3(grid4), dim3(256), 0, st, jobs, n, C / 4));
+  else
+    PGNN_CUDA(pgnn_launch(k_edge_table_bwd_v4<kTblRowsSmall>, dim3(grid4), dim3(256), 0, st, jobs, n, C / 4));
+  PGNN_LAUNCH_CHECK();
+  return PGNN_OK;
+}
+}  // namespace
+
+// several table reductions over the same n rows and C columns in one launch (count <= 4; every job must meet the float4
+// alignment rules, else PGNN_EUNSUPPORTED and the caller issues them one by one)
+int pgnn_internal_edge_table_bwd_batch(int count, const float* const* S, const int* Q, const float* const* g, const int64_t* ldg,
+                                       const int64_t* g_off, float* const* gT, const int64_t* ldt, int64_t n, int C, cudaStream_t st) {
+  if (n == 0 || count == 0) return PGNN_OK;
+  if (!table_v4_enabled() || count > kTblJobs || C % 4) return PGNN_EUNSUPPORTED;
+  TblJobs jobs{};
+  for (int i = 0; i < count; ++i) {
+    if (Q[i] > kMaxQ || ldg[i] % 4 || g_off[i] % 4 || !aligned16(g[i])) return PGNN_EUNSUPPORTED;
+    jobs.j[i] = TblJob{S[i], g[i], gT[i], nullptr, ldg[i], g_off[i], ldt[i], Q[i], Q[i]};
+  }
+  return launch_table_v4(jobs, count, n, C, st);
+}
+
 // shared with gat.cu / encoder.cu: gT[q*ldt + c] += sum_i S[i][q] g[i][g_off + c]  (caller zeroes gT).
 // Rows q >= q_split go to gT2 (the two bond tables of chem/model.py:30-31 are separate parameters).
 int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st) {
   if (n == 0) return PGNN_OK;
   const int rows = n >= 16384 ? kTblRowsLarge : kTblRowsSmall;
+  if (table_v4_enabled() && Q <= kMaxQ && C % 4 == 0 && ldg % 4 == 0 && g_off % 4 == 0 && aligned16(g)) {
+    TblJobs jobs{};
+    jobs.j[0] = TblJob{S, g, gT, gT2, ldg, g_off, ldt, Q, q_split};
+    return launch_table_v4(jobs, 1, n, C, st);
+  }
   dim3 grid((unsigned)ceil_div(n, rows), (unsigned)ceil_div(C, 32));
   PGNN_CUDA(pgnn_launch(k_edge_table_bwd, dim3(grid), dim3(256), 0, st, S, Q, g, ldg, g_off, n, C, gT, ldt, gT2, q_split, rows));
   PGNN_LAUNCH_CHECK();
@@ -447,7 +556,10 @@ int pgnn_bio_embed_bwd(const float* x, const float* g, int64_t ldg, int64_t num_
   PGNN_CUDA(cudaMemsetAsync(gtab, 0, sizeof(float) * 2 * C, st));
   if (num_nodes == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && g);
-  dim3 grid((unsigned)(num_nodes < 64 ? num_nodes : 64), (unsigned)ceil_div(C, 256));
+  // ~32 rows per thread (the row loop is a chain of dependent-latency loads: 64 row blocks took 80 us at N = 32 k)
+  int64_t rb = ceil_div(num_nodes, 32);
+  if (rb > 4 * kNumSMs) rb = 4 * kNumSMs;
+  dim3 grid((unsigned)(rb < 1 ? 1 : rb), (unsigned)ceil_div(C, 256));
   PGNN_CUDA(pgnn_launch(k_bio_embed_bwd, dim3(grid), dim3(256), 0, st, x, g, ldg, num_nodes, (int)C, gtab));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;

@@ -16,6 +16,8 @@
 
 int pgnn_internal_edge_table_bwd(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                  int64_t ldt, cudaStream_t st);
+int pgnn_internal_edge_table_bwd_batch(int count, const float* const* S, const int* Q, const float* const* g, const int64_t* ldg,
+                                       const int64_t* g_off, float* const* gT, const int64_t* ldt, int64_t n, int C, cudaStream_t st);
 
 namespace {
 
@@ -106,6 +108,62 @@ k_gat_fwd(const float* __restrict__ xl, int64_t n, int H, int D, const float* __
     float oacc[kJ];
 #pragma unroll
     for (int j = 0; j < kJ; ++j) oacc[j] = 0.f;
+    if (hi - lo + 1 <= 32) {
+      // Fast path (every molecule node; most PPI nodes): lane m owns message m, so the neighbour id, the edge feature and
+      // the logit are loaded ONCE per node instead of once per pass and head, the softmax runs in registers and the row pass
+      // takes (source, weight) by shuffle.  Same operations in the same order as the general path below: bit-identical.
+      const int cnt = hi - lo + 1, k = lo + lane;
+      const bool act = lane < cnt, real = act && k < hi;
+      const int s = real ? nbr[k] : (int)i;
+      float f[kQ];
+      edge_feat<BIO>(feat, real ? eid[k] : -1, f);
+      for (int h = 0; h < H; ++h) {
+        const float pi = pq[(i * H + h) * 2];
+        float r = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) r = fmaf(f[q], sR[q * kMaxH + h], r);
+        const float lk = leaky(pi + pq[((int64_t)s * H + h) * 2 + 1] + r, slope);
+        const float mx = warp_max(act ? fmaxf(0.f, lk) : 0.f);
+        const float ex = act ? expf(lk - mx) : 0.f;
+        const float inv = 1.f / (warp_sum(ex) + 1e-16f);
+        const float al = ex * inv;
+        if (act) alpha[(real ? (int64_t)k : E + i) * H + h] = al;
+        float A[kQ];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) A[q] = warp_sum(al * f[q]);
+        float acc[kJ];
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) acc[j] = 0.f;
+        for (int m = 0; m < cnt; ++m) {
+          const int sm = __shfl_sync(0xffffffffu, s, m);
+          const float alm = __shfl_sync(0xffffffffu, al, m);
+          const float* row = xl + (int64_t)sm * HD + (int64_t)h * D;
+#pragma unroll
+          for (int j = 0; j < kJ; ++j) {
+            const int c = lane + 32 * j;
+            if (c < D) acc[j] = fmaf(alm, row[c], acc[j]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float* trow = T + (int64_t)q * HD + (int64_t)h * D;
+#pragma unroll
+          for (int j = 0; j < kJ; ++j) {
+            const int c = lane + 32 * j;
+            if (c < D) acc[j] = fmaf(A[q], trow[c], acc[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) oacc[j] += acc[j];
+      }
+      const float invH1 = 1.f / (float)H;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const int c = lane + 32 * j;
+        if (c < D) out[i * ldo + c] = oacc[j] * invH1 + bias[c];
+      }
+      continue;
+    }
     for (int h = 0; h < H; ++h) {
       const float pi = pq[(i * H + h) * 2];
       // pass 1: segment max of the activated logits (lanes over messages; message hi is the self-loop).  The shift starts
@@ -213,6 +271,77 @@ k_gat_bwd_target(const float* __restrict__ g, int64_t ldg, const float* __restri
     for (int j = 0; j < kJ; ++j) {
       const int c = lane + 32 * j;
       gi[j] = c < D ? g[i * ldg + c] * invH : 0.f;
+    }
+    if (hi - lo + 1 <= 32) {
+      // Fast path, as in k_gat_fwd: lane m owns message m (neighbour, edge id, feature, attention weight loaded once per node);
+      // dal_m stays in lane m's register instead of a round trip through dl_e.  Same operations, same order: bit-identical.
+      const int cnt = hi - lo + 1, k = lo + lane;
+      const bool act = lane < cnt, real = act && k < hi;
+      const int s = real ? nbr[k] : (int)i;
+      const int e = real ? eid[k] : -1;
+      float f[kQ];
+      edge_feat<BIO>(feat, e, f);
+      for (int h = 0; h < H; ++h) {
+        float GT[kQ];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float* trow = T + (int64_t)q * HD + (int64_t)h * D;
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < kJ; ++j) {
+            const int c = lane + 32 * j;
+            if (c < D) t = fmaf(gi[j], trow[c], t);
+          }
+          GT[q] = warp_sum(t);
+        }
+        const float al = act ? alpha[(real ? (int64_t)k : E + i) * H + h] : 0.f;
+        float sdot = 0.f, mine = 0.f;
+        for (int m = 0; m < cnt; ++m) {
+          const int sm = __shfl_sync(0xffffffffu, s, m);
+          const float* row = xl + (int64_t)sm * HD + (int64_t)h * D;
+          float d = 0.f;
+#pragma unroll
+          for (int j = 0; j < kJ; ++j) {
+            const int c = lane + 32 * j;
+            if (c < D) d = fmaf(gi[j], row[c], d);
+          }
+          d = warp_sum(d);
+          if (lane == m) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) d = fmaf(f[q], GT[q], d);
+            mine = d;
+          }
+          d = __shfl_sync(0xffffffffu, d, m);
+          sdot = fmaf(__shfl_sync(0xffffffffu, al, m), d, sdot);
+        }
+        const float pi = pq[(i * H + h) * 2];
+        float r = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) r = fmaf(f[q], sR[q * kMaxH + h], r);
+        const float raw = pi + pq[((int64_t)s * H + h) * 2 + 1] + r;
+        const float dl = act ? al * (mine - sdot) * (raw > 0.f ? 1.f : slope) : 0.f;
+        if (act) {
+          const int64_t slot = (e >= 0 ? (int64_t)e : E + i) * H + h;
+          dl_e[slot] = dl;
+          al_e[slot] = al;
+        }
+        const float dp = warp_sum(dl);
+        float A[kQ], B[kQ];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          A[q] = warp_sum(al * f[q]);
+          B[q] = warp_sum(dl * f[q]);
+        }
+        if (lane == 0) {
+          dpq[((int64_t)h * n + i) * 2] = dp;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            Aout[((int64_t)h * n + i) * Q + q] = A[q] * invH;
+            if (B[q] != 0.f) atomicAdd(&Bsum[q * kMaxH + h], B[q]);
+          }
+        }
+      }
+      continue;
     }
     for (int h = 0; h < H; ++h) {
       float GT[kQ];
@@ -446,14 +575,31 @@ int pgnn_gat_bwd(const float* g, int64_t ldg, const float* xl, int64_t num_nodes
   PGNN_CUDA(pgnn_launch(k_gat_bwd_source, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, num_nodes, (int)H, (int)D, att, rowptr_s, nbr_s, eid_s, num_edges,
                                                          w.dl_e, w.al_e, w.dpq, gxl));
   PGNN_LAUNCH_CHECK();
-  for (int h = 0; h < H; ++h) {
-    // message path into the table: gT[:, h, :] = (A_h / H)^T g
-    int rc = pgnn_internal_edge_table_bwd(w.A + (int64_t)h * num_nodes * Q, Q, g, ldg, 0, num_nodes, (int)D, gT + (int64_t)h * D, H * D, st);
-    if (rc != PGNN_OK) return rc;
-    // attention vector: gatt[h, :D] = dp_h^T xl[:, h, :],  gatt[h, D:] = dq_h^T xl[:, h, :]
-    rc = pgnn_internal_edge_table_bwd(w.dpq + (int64_t)h * num_nodes * 2, 2, xl, H * D, (int64_t)h * D, num_nodes, (int)D,
-                                      gatt + (int64_t)h * 2 * D, D, st);
-    if (rc != PGNN_OK) return rc;
+  // message path into the table: gT[:, h, :] = (A_h / H)^T g;  attention vector: gatt[h, :D] = dp_h^T xl[:, h, :],
+  // gatt[h, D:] = dq_h^T xl[:, h, :] -- 2 H reductions over the same rows, batched into one launch when H <= 2
+  {
+    int batched = PGNN_EUNSUPPORTED;
+    if (2 * H <= 4) {
+      const float* Sp[4]; const float* gp[4]; float* op[4];
+      int Qs[4]; int64_t ldgs[4], goffs[4], ldts[4];
+      for (int h = 0; h < (int)H; ++h) {
+        Sp[2 * h] = w.A + (int64_t)h * num_nodes * Q; Qs[2 * h] = Q; gp[2 * h] = g; ldgs[2 * h] = ldg; goffs[2 * h] = 0;
+        op[2 * h] = gT + (int64_t)h * D; ldts[2 * h] = H * D;
+        Sp[2 * h + 1] = w.dpq + (int64_t)h * num_nodes * 2; Qs[2 * h + 1] = 2; gp[2 * h + 1] = xl; ldgs[2 * h + 1] = H * D;
+        goffs[2 * h + 1] = (int64_t)h * D; op[2 * h + 1] = gatt + (int64_t)h * 2 * D; ldts[2 * h + 1] = D;
+      }
+      batched = pgnn_internal_edge_table_bwd_batch((int)(2 * H), Sp, Qs, gp, ldgs, goffs, op, ldts, num_nodes, (int)D, st);
+      if (batched != PGNN_OK && batched != PGNN_EUNSUPPORTED) return batched;
+    }
+    if (batched == PGNN_EUNSUPPORTED) {
+      for (int h = 0; h < H; ++h) {
+        int rc = pgnn_internal_edge_table_bwd(w.A + (int64_t)h * num_nodes * Q, Q, g, ldg, 0, num_nodes, (int)D, gT + (int64_t)h * D, H * D, st);
+        if (rc != PGNN_OK) return rc;
+        rc = pgnn_internal_edge_table_bwd(w.dpq + (int64_t)h * num_nodes * 2, 2, xl, H * D, (int64_t)h * D, num_nodes, (int)D,
+                                          gatt + (int64_t)h * 2 * D, D, st);
+        if (rc != PGNN_OK) return rc;
+      }
+    }
   }
   PGNN_CUDA(pgnn_launch(k_gat_bwd_rterm, dim3((unsigned)ceil_div(H * D, 128)), dim3(128), 0, st, w.Bsum, att, T, Q, (int)H, (int)D, gatt, gT));
   PGNN_LAUNCH_CHECK();

@@ -408,6 +408,34 @@ k_relu_bwd(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__
   }
 }
 
+// float4 variants (rows 16-byte aligned, C % 4 == 0): one 64-bit division per FOUR elements instead of one per element, 16-byte
+// accesses.  The scalar kernels ran at ~2.5 TB/s on the bio step's [32 k, 300] activations (180 us per step for four ReLU backward sweeps).
+__global__ void __launch_bounds__(256)
+k_relu_fwd_v4(const float* __restrict__ x, int64_t ldx, int64_t M, int C4, float* __restrict__ y, int64_t ldy) {
+  pdl_prologue();
+  const int64_t total = M * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C4;
+    const int c = (int)(idx - r * C4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    *reinterpret_cast<float4*>(y + r * ldy + c) = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+  }
+}
+__global__ void __launch_bounds__(256)
+k_relu_bwd_v4(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ y, int64_t ldy, int64_t M, int C4,
+              float* __restrict__ gx, int64_t ldgx) {
+  pdl_prologue();
+  const int64_t total = M * C4;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / C4;
+    const int c = (int)(idx - r * C4) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gy + r * ldgy + c);
+    const float4 v = *reinterpret_cast<const float4*>(y + r * ldy + c);
+    *reinterpret_cast<float4*>(gx + r * ldgx + c) =
+        make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f);
+  }
+}
+
 // one warp per row
 __global__ void __launch_bounds__(256)
 k_l2norm_fwd(const float* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ y, int64_t ldy,
@@ -579,6 +607,11 @@ int pgnn_relu_fwd(const float* x, int64_t ldx, int64_t M, int64_t C, float* y, i
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(x && y);
+  if (C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    PGNN_CUDA(pgnn_launch(k_relu_fwd_v4, dim3(grid_items(M * (C / 4), 256)), dim3(256), 0, as_stream(stream), x, ldx, M, (int)(C / 4), y, ldy));
+    PGNN_LAUNCH_CHECK();
+    return PGNN_OK;
+  }
   PGNN_CUDA(pgnn_launch(k_relu_fwd, dim3(grid_items(M * C, 256)), dim3(256), 0, as_stream(stream), x, ldx, M, (int)C, y, ldy));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;
@@ -589,6 +622,12 @@ int pgnn_relu_bwd(const float* gy, int64_t ldgy, const float* y, int64_t ldy_, i
   PGNN_CHECK_ARG(M >= 0 && C > 0);
   if (M == 0) return PGNN_OK;
   PGNN_CHECK_ARG(gy && y && gx);
+  if (C % 4 == 0 && ldgy % 4 == 0 && ldy_ % 4 == 0 && ldgx % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gx)) & 15) == 0) {
+    PGNN_CUDA(pgnn_launch(k_relu_bwd_v4, dim3(grid_items(M * (C / 4), 256)), dim3(256), 0, as_stream(stream), gy, ldgy, y, ldy_, M, (int)(C / 4), gx, ldgx));
+    PGNN_LAUNCH_CHECK();
+    return PGNN_OK;
+  }
   PGNN_CUDA(pgnn_launch(k_relu_bwd, dim3(grid_items(M * C, 256)), dim3(256), 0, as_stream(stream), gy, ldgy, y, ldy_, M, (int)C, gx, ldgx));
   PGNN_LAUNCH_CHECK();
   return PGNN_OK;

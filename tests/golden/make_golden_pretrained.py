@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference):
 
     python tests/golden/make_golden_pretrained.py
 
-Stored per case: the reference's eval-mode node representations `[N, 300]` fp32 (a train-mode forward would overwrite nothing
+Stored per case: the reference's eval-mode node representations `[N, 300]` fp32 and fp64 (a train-mode forward would overwrite nothing
 here, but the checkpoints' BatchNorm running statistics are what eval mode exercises), an input checksum, and a SHA-256 of the
 checkpoint file so the test can tell a wrong staged file from a wrong kernel.  The weights themselves are never committed:
 `oracle/reference_runner.stage()` copies the checkpoint files next to the staged model.py (git-ignored `oracle/_ref/weights/`),
@@ -46,6 +46,15 @@ def main():
         with torch.no_grad():
             y = model(b["x"], b["edge_index"], b["edge_attr"])
         out[name + ":out_eval"] = y.numpy()
+        # the same forward in float64: the yardstick for how well conditioned the checkpoint is (the trained GIN's pre-BatchNorm
+        # activations reach 1e5, and eval-mode BatchNorm turns a uniform absolute error of the Linear output into per-column errors)
+        m64 = ref.GNN(5, 300, JK="last", drop_ratio=0, gnn_type=c["type"])
+        m64.load_state_dict(sd)
+        m64.double().eval()
+        with torch.no_grad():
+            y64 = m64(b["x"].double() if b["x"].is_floating_point() else b["x"], b["edge_index"],
+                      b["edge_attr"].double() if b["edge_attr"].is_floating_point() else b["edge_attr"])
+        out[name + ":d64"] = (y64 - y.double()).float().numpy()     # ref64 = out_eval + d64 (the difference is tiny: stored in fp32)
         out[name + ":input_checksum"] = input_checksum(b)
         out[name + ":sha256"] = np.frombuffer(hashlib.sha256(open(path, "rb").read()).digest(), dtype=np.uint8)
         print("%-14s N = %5d  max|out| = %8.3f  %s" % (name, y.shape[0], float(y.abs().max()), c["file"]))
