@@ -108,62 +108,6 @@ k_gat_fwd(const float* __restrict__ xl, int64_t n, int H, int D, const float* __
     float oacc[kJ];
 #pragma unroll
     for (int j = 0; j < kJ; ++j) oacc[j] = 0.f;
-    if (hi - lo + 1 <= 32) {
-      // Fast path (every molecule node; most PPI nodes): lane m owns message m, so the neighbour id, the edge feature and
-      // the logit are loaded ONCE per node instead of once per pass and head, the softmax runs in registers and the row pass
-      // takes (source, weight) by shuffle.  Same operations in the same order as the general path below: bit-identical.
-      const int cnt = hi - lo + 1, k = lo + lane;
-      const bool act = lane < cnt, real = act && k < hi;
-      const int s = real ? nbr[k] : (int)i;
-      float f[kQ];
-      edge_feat<BIO>(feat, real ? eid[k] : -1, f);
-      for (int h = 0; h < H; ++h) {
-        const float pi = pq[(i * H + h) * 2];
-        float r = 0.f;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) r = fmaf(f[q], sR[q * kMaxH + h], r);
-        const float lk = leaky(pi + pq[((int64_t)s * H + h) * 2 + 1] + r, slope);
-        const float mx = warp_max(act ? fmaxf(0.f, lk) : 0.f);
-        const float ex = act ? expf(lk - mx) : 0.f;
-        const float inv = 1.f / (warp_sum(ex) + 1e-16f);
-        const float al = ex * inv;
-        if (act) alpha[(real ? (int64_t)k : E + i) * H + h] = al;
-        float A[kQ];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) A[q] = warp_sum(al * f[q]);
-        float acc[kJ];
-#pragma unroll
-        for (int j = 0; j < kJ; ++j) acc[j] = 0.f;
-        for (int m = 0; m < cnt; ++m) {
-          const int sm = __shfl_sync(0xffffffffu, s, m);
-          const float alm = __shfl_sync(0xffffffffu, al, m);
-          const float* row = xl + (int64_t)sm * HD + (int64_t)h * D;
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) {
-            const int c = lane + 32 * j;
-            if (c < D) acc[j] = fmaf(alm, row[c], acc[j]);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float* trow = T + (int64_t)q * HD + (int64_t)h * D;
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) {
-            const int c = lane + 32 * j;
-            if (c < D) acc[j] = fmaf(A[q], trow[c], acc[j]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < kJ; ++j) oacc[j] += acc[j];
-      }
-      const float invH1 = 1.f / (float)H;
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        const int c = lane + 32 * j;
-        if (c < D) out[i * ldo + c] = oacc[j] * invH1 + bias[c];
-      }
-      continue;
-    }
     for (int h = 0; h < H; ++h) {
       const float pi = pq[(i * H + h) * 2];
       // pass 1: segment max of the activated logits (lanes over messages; message hi is the self-loop).  The shift starts
@@ -225,8 +169,11 @@ k_gat_fwd(const float* __restrict__ xl, int64_t n, int H, int D, const float* __
           if (c < D) acc[j] = fmaf(al, row[c], acc[j]);
         }
       }
+      // a molecule node sees 3-5 of the 9 one-hot feature values: rows with A[q] == 0 (warp-uniform, A is warp-reduced) add
+      // nothing and are skipped -- the table rows were more than half of this kernel's L1/L2 traffic
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
+        if (A[q] == 0.f) continue;
         const float* trow = T + (int64_t)q * HD + (int64_t)h * D;
 #pragma unroll
         for (int j = 0; j < kJ; ++j) {
@@ -272,81 +219,23 @@ k_gat_bwd_target(const float* __restrict__ g, int64_t ldg, const float* __restri
       const int c = lane + 32 * j;
       gi[j] = c < D ? g[i * ldg + c] * invH : 0.f;
     }
-    if (hi - lo + 1 <= 32) {
-      // Fast path, as in k_gat_fwd: lane m owns message m (neighbour, edge id, feature, attention weight loaded once per node);
-      // dal_m stays in lane m's register instead of a round trip through dl_e.  Same operations, same order: bit-identical.
-      const int cnt = hi - lo + 1, k = lo + lane;
-      const bool act = lane < cnt, real = act && k < hi;
-      const int s = real ? nbr[k] : (int)i;
-      const int e = real ? eid[k] : -1;
+    // feature columns that any message of this node carries (bit q): GT[q] multiplies f_k[q] only, so the other dot products
+    // (each a 300-wide row of T and five shuffles per head) are skipped; a molecule node uses 3-5 of the 9
+    unsigned used = 0u;
+    for (int k = lo + lane; k <= hi; k += 32) {
       float f[kQ];
-      edge_feat<BIO>(feat, e, f);
-      for (int h = 0; h < H; ++h) {
-        float GT[kQ];
+      edge_feat<BIO>(feat, k < hi ? eid[k] : -1, f);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float* trow = T + (int64_t)q * HD + (int64_t)h * D;
-          float t = 0.f;
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) {
-            const int c = lane + 32 * j;
-            if (c < D) t = fmaf(gi[j], trow[c], t);
-          }
-          GT[q] = warp_sum(t);
-        }
-        const float al = act ? alpha[(real ? (int64_t)k : E + i) * H + h] : 0.f;
-        float sdot = 0.f, mine = 0.f;
-        for (int m = 0; m < cnt; ++m) {
-          const int sm = __shfl_sync(0xffffffffu, s, m);
-          const float* row = xl + (int64_t)sm * HD + (int64_t)h * D;
-          float d = 0.f;
-#pragma unroll
-          for (int j = 0; j < kJ; ++j) {
-            const int c = lane + 32 * j;
-            if (c < D) d = fmaf(gi[j], row[c], d);
-          }
-          d = warp_sum(d);
-          if (lane == m) {
-#pragma unroll
-            for (int q = 0; q < Q; ++q) d = fmaf(f[q], GT[q], d);
-            mine = d;
-          }
-          d = __shfl_sync(0xffffffffu, d, m);
-          sdot = fmaf(__shfl_sync(0xffffffffu, al, m), d, sdot);
-        }
-        const float pi = pq[(i * H + h) * 2];
-        float r = 0.f;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) r = fmaf(f[q], sR[q * kMaxH + h], r);
-        const float raw = pi + pq[((int64_t)s * H + h) * 2 + 1] + r;
-        const float dl = act ? al * (mine - sdot) * (raw > 0.f ? 1.f : slope) : 0.f;
-        if (act) {
-          const int64_t slot = (e >= 0 ? (int64_t)e : E + i) * H + h;
-          dl_e[slot] = dl;
-          al_e[slot] = al;
-        }
-        const float dp = warp_sum(dl);
-        float A[kQ], B[kQ];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          A[q] = warp_sum(al * f[q]);
-          B[q] = warp_sum(dl * f[q]);
-        }
-        if (lane == 0) {
-          dpq[((int64_t)h * n + i) * 2] = dp;
-#pragma unroll
-          for (int q = 0; q < Q; ++q) {
-            Aout[((int64_t)h * n + i) * Q + q] = A[q] * invH;
-            if (B[q] != 0.f) atomicAdd(&Bsum[q * kMaxH + h], B[q]);
-          }
-        }
-      }
-      continue;
+      for (int q = 0; q < Q; ++q) used |= (f[q] != 0.f) ? (1u << q) : 0u;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) used |= __shfl_xor_sync(0xffffffffu, used, o);
     for (int h = 0; h < H; ++h) {
       float GT[kQ];
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
+        GT[q] = 0.f;
+        if (!((used >> q) & 1u)) continue;
         const float* trow = T + (int64_t)q * HD + (int64_t)h * D;
         float s = 0.f;
 #pragma unroll
