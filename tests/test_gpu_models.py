@@ -380,14 +380,14 @@ def test_module_with_shipped_checkpoint_matches_reference_golden(name, fused, pr
     git-ignored oracle/_ref/weights by build()) and reproduces the reference's own eval-mode output on the same batch.
     chem GIN masking.pth at B = 32 is config 1; the GCN checkpoint's activations reach |x| ~ 190.
 
-    Bars.  Every case: max |mine - ref64| <= OUT_REL (4e-5, the bar of the full-size parity tests) of the tensor's scale.  GAT,
-    GraphSAGE and bio GIN also meet the element-wise north_star bound |mine - ref32| <= 1e-4 + 1e-4 |ref32| and it is asserted.
-    The trained chem GIN / GCN encoders are ILL-CONDITIONED at that bound: their pre-BatchNorm activations reach 1.1e5 (GIN,
-    layer 0) and eval-mode BatchNorm (running statistics) maps the Linear output's uniform absolute error onto columns whose
-    gamma / sigma differ by orders of magnitude; the reference's own fp32 run misses its fp64 run by 2.3e-5 (GIN) and 2.5e-4
-    (GCN) absolute.  For those two the fraction of elements inside the north_star bound is measured and reported
-    (gpurun_out/parity/pretrained_*.json), not asserted; `precision = fp32` (the exact FFMA kernels) is measured beside the
-    3xTF32 tensor path, whose accumulators round toward zero (profiles/r02_parity_errors.md)."""
+    Bars (measured values in profiles/r02_parity_errors.md).  Every case: max |mine - ref64| <= OUT_REL (4e-5, the bar of the
+    full-size parity tests) of the tensor's scale.  `precision = fp32` (the exact FFMA kernels): the element-wise north_star bound
+    |mine - ref32| <= 1e-4 + 1e-4 |ref32| holds on EVERY checkpoint and is asserted (measured: the error equals the reference's
+    own fp32-vs-fp64 discrepancy, 1e-6 of scale).  The default 3xTF32 tensor path meets it on GAT, GraphSAGE and bio GIN (asserted);
+    on the trained chem GIN / GCN encoders it is held to >= 99.9 % of the elements (measured 99.999 % / 99.91 %, max error 2.0e-5 /
+    4.3e-6 of scale): their pre-BatchNorm activations reach 1.1e5 (GIN layer 0) and eval-mode BatchNorm maps the Linear output's
+    absolute error onto columns whose gamma / sigma differ by orders of magnitude, which exposes that the tensor core's fp32
+    accumulation is less exact than an FMA chain (20x the FFMA path's error on these weights, 1-3x on seeded ones)."""
     import hashlib
     import numpy as np
     import os
@@ -418,5 +418,7 @@ def test_module_with_shipped_checkpoint_matches_reference_golden(name, fused, pr
                  [dict(kind="out", name="node_rep", err=e64, err_ref32=eref, north_star=bool(inside.all()), ok=e64 <= OUT_REL)],
                  dict(scale=scale, max_abs_err=e64 * scale, ref32_vs_ref64_abs=eref * scale, fraction_inside_north_star=frac))
     assert e64 <= OUT_REL, (e64, eref, scale)
-    if name not in ("chem_gin", "chem_gcn"):
+    if precision == "fp32" or name not in ("chem_gin", "chem_gcn"):
         assert bool(inside.all()), (float((out - ref32).abs().max()), scale, frac)
+    else:
+        assert frac >= 0.999, (frac, e64, scale)
