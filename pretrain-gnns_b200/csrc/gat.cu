@@ -14,6 +14,8 @@
 // scalar work; no atomics except the handful that fold Q*H scalars.
 #include "common.cuh"
 
+#include <cstdlib>
+
 int pgnn_internal_edge_table_bwd(const float* S, int Q, const float* g, int64_t ldg, int64_t g_off, int64_t n, int C, float* gT,
                                  int64_t ldt, cudaStream_t st);
 int pgnn_internal_edge_table_bwd_batch(int count, const float* const* S, const int* Q, const float* const* g, const int64_t* ldg,
@@ -197,8 +199,8 @@ k_gat_fwd(const float* __restrict__ xl, int64_t n, int H, int D, const float* __
 //   dal_k = <g_i/H, x_j'>,  dl_k = a_k (dal_k - sum_m a_m dal_m) * leaky'(raw_k)
 // writes dl and a indexed by ORIGINAL edge id (self-loop of i at E+i) for the source-side pass, dp[i,h],
 // the scaled summary A[h][i][:] (for gT) and folds B[q][h] = sum dl_k f_k[q] into Bsum.
-template <bool BIO>
-__global__ void __launch_bounds__(256)
+template <bool BIO, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_gat_bwd_target(const float* __restrict__ g, int64_t ldg, const float* __restrict__ xl, int64_t n, int H, int D,
                  const float* __restrict__ att, const float* __restrict__ T, const void* __restrict__ feat,
                  const int* __restrict__ rowptr, const int* __restrict__ nbr, const int* __restrict__ eid, int64_t E, float slope,
@@ -454,12 +456,18 @@ int pgnn_gat_bwd(const float* g, int64_t ldg, const float* xl, int64_t num_nodes
   if (workspace_bytes < pgnn_gat_bwd_workspace_bytes(num_nodes, num_edges, H, D)) return PGNN_EWORKSPACE;
   BwdWs w = carve(workspace, num_nodes, num_edges, H);
   PGNN_CUDA(cudaMemsetAsync(w.Bsum, 0, sizeof(float) * kQ * kMaxH, st));
-  if (is_bio)
-    PGNN_CUDA(pgnn_launch(k_gat_bwd_target<true>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t,
-                                                                 eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum));
-  else
-    PGNN_CUDA(pgnn_launch(k_gat_bwd_target<false>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, xl, num_nodes, (int)H, (int)D, att, T, feat, rowptr_t, nbr_t,
-                                                                  eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum));
+  // PGNN_GAT_OCC=1: the 64-register build (four resident CTAs per SM instead of three; the kernel is a chain of dependent loads per
+  // warp, so resident warps are what it is short of) -- measured against the default in profiles/README.md
+  static const bool occ4 = getenv("PGNN_GAT_OCC") && getenv("PGNN_GAT_OCC")[0] == '1';
+#define PGNN_GAT_BT(BIO_, MINB_)                                                                                                          \
+  PGNN_CUDA(pgnn_launch(k_gat_bwd_target<BIO_, MINB_>, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, xl, num_nodes, (int)H, (int)D, att, T, \
+                        feat, rowptr_t, nbr_t, eid_t, num_edges, slope, alpha, pq, w.dl_e, w.al_e, w.dpq, w.A, w.Bsum))
+  if (is_bio) {
+    if (occ4) PGNN_GAT_BT(true, 4); else PGNN_GAT_BT(true, 3);
+  } else {
+    if (occ4) PGNN_GAT_BT(false, 4); else PGNN_GAT_BT(false, 3);
+  }
+#undef PGNN_GAT_BT
   PGNN_LAUNCH_CHECK();
   PGNN_CUDA(pgnn_launch(k_gat_bwd_source, dim3(warp_grid(num_nodes)), dim3(256), 0, st, g, ldg, num_nodes, (int)H, (int)D, att, rowptr_s, nbr_s, eid_s, num_edges,
                                                          w.dl_e, w.al_e, w.dpq, gxl));

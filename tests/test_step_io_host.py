@@ -103,3 +103,32 @@ def test_batch_stager_roundtrip_cpu():
         ticket = st.submit(packed[(i + 1) % 5])      # prefetch: must not disturb the batch in use
         for k, v in batches[i].items():
             assert got[k].dtype == v.dtype and got[k].shape == v.shape and torch.equal(got[k], v), (i, k)
+
+
+def test_pair_first_flags_match_the_oracle_and_odd_edge_counts_are_rejected():
+    """data._pair_first (host, once per store): first occurrence of every unordered bond per graph, as networkx keeps them
+    (chem/loader.py:173), against oracle.first_pairs graph by graph; a graph with an odd number of edge columns is refused."""
+    data = importlib.import_module("pretrain-gnns_b200.data")
+    graphs = syn.split_graphs(syn.zinc_batch(30, 5))
+    edge_ptr = np.concatenate([[0], np.cumsum([g[1].shape[1] for g in graphs])])
+    ei = np.concatenate([g[1] for g in graphs], axis=1)
+    flags = data._pair_first(edge_ptr, ei)
+    ref = np.concatenate([SO.first_pairs(g[1]) for g in graphs]).astype(np.uint8)
+    assert np.array_equal(flags, ref) and 0 < int((1 - flags).sum()) < len(flags) // 4    # the generator does repeat a few bonds
+    with pytest.raises(ValueError):
+        data._pair_first(np.array([0, 3]), ei[:, :3])
+
+
+def test_transform_size_queries_on_the_host():
+    """The host-side size functions of the f4 entry points (no GPU involved): pgnn_mask_edges_bio_count equals the oracle's draw
+    sizes (int(e/2 * rate + 1) per graph, 0 for a graph without edges), the workspace queries grow with their arguments and
+    refuse negative sizes."""
+    import ctypes
+    cabi = importlib.import_module("pretrain-gnns_b200._cabi")
+    dll = cabi.lib.load()
+    edge_off = np.array([0, 40, 40, 46, 1046], dtype=np.int64)
+    n = dll.pgnn_mask_edges_bio_count(edge_off.ctypes.data_as(ctypes.c_void_p), 4, 0.15)
+    assert n == sum(len(c) for c in SO.mask_edge_choice_bio(edge_off, 0.15, seed=1)) == 4 + 0 + 1 + 76
+    assert dll.pgnn_extract_pairs_workspace_bytes(8, 200) < dll.pgnn_extract_pairs_workspace_bytes(8, 4000)
+    assert dll.pgnn_extract_pairs_workspace_bytes(-1, 10) < 0 and dll.pgnn_mask_edges_chem_workspace_bytes(-1, 1) < 0
+    assert dll.pgnn_mask_edges_chem_workspace_bytes(6000, 256) >= 6000 + 256 * 8
