@@ -412,14 +412,24 @@ def run_b200(args, rank, world, local_rank):
         timed.host_issue_ms = [1e3 * (b - a) for a, b in zip(host_t[:-1], host_t[1:])]  # host time per loop iteration (diagnostic)
         t = torch.tensor([sum(per)], dtype=torch.float64, device=dev)
         if world > 1:
+            # every rank's own figures (sum, slowest step and its index), so that a slow rank can be told from a slow step
+            mine = torch.tensor([sum(per), max(per), float(per.index(max(per))), sorted(per)[len(per) // 2]], dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            timed.per_rank = [dict(rank=r, ms_per_step=float(v[0]) / max(args.steps, 1), median_ms=float(v[3]), slowest_ms=float(v[1]),
+                                   slowest_step=int(v[2])) for r, v in enumerate(allr)]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        else:
+            timed.per_rank = None
         return float(t.item()), launches, wall, per, acc / max(args.steps, 1)
 
     with ClockSampler(local_rank) as clocks:
         ms_dev, launches, wall_dev, per_dev, _ = timed(False)
         host_dev = timed.host_issue_ms
+        per_rank_dev = timed.per_rank
         ms_e2e, _, wall_e2e, per_e2e, mean_loss = timed(True)
         host_e2e = timed.host_issue_ms
+        per_rank_e2e = timed.per_rank
     graphs = B * world * args.steps
     wm = work_model(config, host[0])
 
@@ -451,6 +461,7 @@ def run_b200(args, rank, world, local_rank):
                    "slowest_steps": [(round(t, 3), i, round(host_dev[i], 3)) for t, i in sorted(((t, i) for i, t in enumerate(per_dev)), reverse=True)[:4]],
                    "slowest_e2e_steps": [(round(t, 3), i, round(host_e2e[i], 3)) for t, i in sorted(((t, i) for i, t in enumerate(per_e2e)), reverse=True)[:4]],
                    "slowest_steps_fields": "[device ms, step index, host ms spent issuing that loop iteration]",
+                   "per_rank": per_rank_dev, "per_rank_e2e": per_rank_e2e,
                    "wall_ms_per_step_incl_flush": 1e3 * wall_dev / args.steps, "wall_ms_per_step_incl_flush_e2e": 1e3 * wall_e2e / args.steps,
                    "mean_loss_e2e": mean_loss, "gemm_flops_per_step": wm["gemm_flops_per_step"]},
         "e2e": {"value": graphs / (ms_e2e * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

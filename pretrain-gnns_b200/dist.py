@@ -55,7 +55,9 @@ def _unpack(views, params):
 class P2PAllReduce:
     """Symmetric fp32 buffers of `numel` elements plus the flag words of the library's NVLink all-reduces.
 
-    mode (argument, else PGNN_ALLREDUCE, else "fused"):
+    mode (argument, else PGNN_ALLREDUCE, else "p2p"; measured at 2 GPUs on the masking step, 50 steps, max over ranks: p2p 415 k graphs/s,
+    fused 357 k, nvls 346 k -- the one-kernel variants have the better median step (1.183 / 1.192 vs 1.196 ms on rank 0) but one rank
+    carries ~12 ms more inside its timed steps, not yet explained; bench.py now reports every rank's figures):
       "fused"   one kernel, out of place (`pgnn_allreduce_fused`): gradients are written into `buf`, the mean lands in `out`
       "nvls"    the same kernel with the NVSwitch doing the sum (multimem.ld_reduce / multimem.st on the multicast mappings);
                 falls back to "fused" when the allocation has no multicast mapping
@@ -70,7 +72,7 @@ class P2PAllReduce:
         from ._cabi import lib
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world, self.numel = dist.get_rank(group), dist.get_world_size(group), int(numel)
-        mode = mode or os.environ.get("PGNN_ALLREDUCE", "") or "fused"
+        mode = mode or os.environ.get("PGNN_ALLREDUCE", "") or "p2p"
         if mode not in ("fused", "nvls", "p2p"):
             raise ValueError("PGNN_ALLREDUCE must be fused, nvls or p2p")
         quantum = 4 * self.world
@@ -157,7 +159,7 @@ class GradAllReducer:
         if backend != "nccl" and on_cuda and dist.get_world_size(group) > 1:
             try:
                 self._setup_p2p(all_params[0].device)
-                self.backend = self.p2p.transport  # "fused" (default), "nvls" or "p2p"
+                self.backend = self.p2p.transport  # "p2p" (default), "fused" or "nvls"
             except Exception as e:  # no peer access / symmetric memory unavailable on this box
                 if backend == "p2p":
                     raise

@@ -23,6 +23,12 @@ timeout -s KILL 300 python bench.py --config masking --precision fp32 --steps 30
 python -c "
 import json
 d=json.loads(open('gpurun_out/bench_masking_fp32.json').read().strip().splitlines()[-1]); print('masking --precision fp32', round(d['value']), round(d['ms_per_step'],4))" || tail -3 gpurun_out/bench_masking_fp32.err
+PGNN_GAT_OCC=1 timeout -s KILL 300 python bench.py --config gat --steps 30 --no-cpu-baseline > gpurun_out/bench_gat_occ4.json 2> gpurun_out/bench_gat_occ4.err
+python -c "
+import json
+for f in ('gpurun_out/bench_gat.json', 'gpurun_out/bench_gat_occ4.json'):
+    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, round(d['value']), round(d['ms_per_step'],4), {k:v for k,v in d['roofline']['step_kernels_us'].items() if 'gat' in k})"
+timeout -s KILL 120 python tools/host_profile.py --config gcn --steps 40 > gpurun_out/host_profile_gcn.txt 2>&1; head -16 gpurun_out/host_profile_gcn.txt
 # ncu launch lists (shares), then one full capture of the masking step's GEMM family + gathers + BatchNorm-backward sweeps
 for c in masking bio_supervised gat; do
   timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
