@@ -225,8 +225,9 @@ k_edge_table_bwd(const float* __restrict__ S, int Q, const float* __restrict__ g
 }
 
 // float4 variant of k_edge_table_bwd: a lane owns FOUR adjacent columns (512-byte warp loads: a quarter of the load instructions
-// per byte) and the CTA's S rows are staged in shared memory once (coalesced) instead of Q broadcast loads per row and thread --
-// the scalar kernel issues 1 + Q load instructions per 128 useful bytes and is instruction-bound (59 us for 38 MB at N = 32 k).
+// per byte) and the CTA's S rows are staged in shared memory once (coalesced) instead of Q broadcast loads per row and thread.
+// Measured: no faster than the scalar kernel for ONE reduction (the hypothesis that the scalar kernel is load-instruction bound
+// was wrong: 58.9 vs 55.6 us at N = 32 k); it is used for the batched form below, where it saves launches.
 // 8 row-lanes x 32 column-lanes; the row-lanes are folded through shared memory eight table rows at a time.
 // Up to kTblJobs reductions over the same n rows in ONE launch (blockIdx.z): the GAT backward needs four per layer (two heads x
 // {message table, attention vector}), each a ~6 us kernel on a molecule batch.
@@ -430,7 +431,11 @@ int pgnn_internal_edge_table_bwd2(const float* S, int Q, const float* g, int64_t
                                   int64_t ldt, float* gT2, int q_split, cudaStream_t st) {
   if (n == 0) return PGNN_OK;
   const int rows = n >= 16384 ? kTblRowsLarge : kTblRowsSmall;
-  if (table_v4_enabled() && Q <= kMaxQ && C % 4 == 0 && ldg % 4 == 0 && g_off % 4 == 0 && aligned16(g)) {
+  // A single reduction stays on the scalar kernel: the float4 kernel measured no faster alone (bio N = 32 k: 58.9 vs 55.6 us per
+  // launch under ncu, 317 vs 296 us per step in the step; GCN: 79 vs 76) -- what it buys is the batching of several reductions
+  // into one launch (pgnn_internal_edge_table_bwd_batch, the GAT backward).  PGNN_TABLE_V4=1 forces it here as well.
+  static const bool force_v4 = getenv("PGNN_TABLE_V4") && getenv("PGNN_TABLE_V4")[0] == '1';
+  if (force_v4 && Q <= kMaxQ && C % 4 == 0 && ldg % 4 == 0 && g_off % 4 == 0 && aligned16(g)) {
     TblJobs jobs{};
     jobs.j[0] = TblJob{S, g, gT, gT2, ldg, g_off, ldt, Q, q_split};
     return launch_table_v4(jobs, 1, n, C, st);

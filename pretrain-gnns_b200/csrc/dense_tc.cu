@@ -637,7 +637,9 @@ int pgnn_tc_linear_bwd_w_ws2(const float* gy, int64_t ldgy, const float* x, int6
   if (gb) {
     PGNN_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * N, st));
     const int rows_per = M >= 16384 ? 256 : 64;  // 8 rows per thread for small batches: the row loop is a latency chain
-    if (M >= 16384 && N % 4 == 0 && ldgy % 4 == 0 && aligned16(gy)) {  // small batches: the scalar kernel's 4x more CTAs win (measured)
+    // the float4 variant measured slower at both sizes (N = 6 k: 51.6 vs 45.9 us per step; N = 32 k: 16.1 vs 14.1 us per launch): opt-in only
+    static const bool colsum_v4 = getenv("PGNN_COLSUM_V4") && getenv("PGNN_COLSUM_V4")[0] == '1';
+    if (colsum_v4 && N % 4 == 0 && ldgy % 4 == 0 && aligned16(gy)) {
       dim3 g4((unsigned)ceil_div(N / 4, 32), (unsigned)ceil_div(M, rows_per));
       PGNN_CUDA(pgnn_launch(k_colsum_tc_v4, dim3(g4), dim3(256), 0, st, gy, ldgy, (int)M, (int)(N / 4), rows_per, gb));
       PGNN_LAUNCH_CHECK();
