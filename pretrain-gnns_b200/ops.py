@@ -57,7 +57,15 @@ def raise_on_device_errors():
 _VALIDATE = os.environ.get("PGNN_VALIDATE", "") == "1"
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _st():
+    """cudaStream_t of torch's current stream on the current device.  The raw accessor (the one triton's launcher uses) costs ~0.3 us
+    against ~4 us for building a torch.cuda.Stream object: every op calls this, eight to thirty times per training step."""
+    if _raw_stream is not None and _cur_device is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 
