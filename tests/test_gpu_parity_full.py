@@ -190,8 +190,8 @@ def test_loss_heads_vs_torch_fp64():
 @pytest.mark.parametrize("config", ["masking", "gcn", "gat"])
 def test_training_step_run_to_run_reproducibility(config):
     """Two training steps on the same batch and parameters.  The loss (ordered fp64 fold) must repeat to 1e-9; every gradient must
-    repeat to 2e-5 of its scale (the tensor's own largest magnitude, floored at 1e-3 of the model's largest gradient so that the
-    structurally-zero biases in front of train-mode BatchNorm are judged on the model's scale).  What is ordered by construction --
+    repeat to 2e-5 of its scale (the tensor's own largest magnitude; the structurally-zero biases in front of train-mode BatchNorm
+    on the model's largest gradient).  Measured: <= 3.5e-6; 17 of 44 (GIN, GAT) / 34 (GCN) tensors bit-identical.  What is ordered by construction --
     weight and embedding-table gradients from split-K partial tiles folded in split order -- is expected BIT-identical, the
     bias / BatchNorm / bond-table gradients and the GAT scalar folds go through fp32 / fp64 atomics whose order varies: the number
     of bit-identical tensors and the worst difference are MEASURED and reported (gpurun_out/parity/reproducibility_*.json,
@@ -211,7 +211,10 @@ def test_training_step_run_to_run_reproducibility(config):
     rows, bitwise, worst = [], 0, 0.0
     gmax = max(float(v.abs().max()) for v in g0.values())
     for k in g0:
-        scale = max(float(g0[k].abs().max()), 1e-3 * gmax, 1e-30)
+        tmax = float(g0[k].abs().max())
+        # a bias in front of train-mode BatchNorm (mlp.2.bias, GAT's bias / weight_linear.bias) has a structurally zero gradient: what
+        # is computed is cancellation noise (< 1e-3 of the model's largest gradient) and is judged on the model's scale
+        scale = max(gmax if tmax < 1e-3 * gmax else tmax, 1e-30)
         diff = float((g0[k] - g1[k]).abs().max()) / scale
         same = bool(torch.equal(g0[k], g1[k]))
         bitwise += same
